@@ -1,0 +1,245 @@
+// kernels_synth.cu — device-side synthetic OPV channel bank (measurement aid).
+//
+// A B200-resident restatement of the opv-mod transmit chain (/root/reference/src/opv-mod.cpp:
+// BERT frame :339-361, randomise + K=7 encoder + 67x32 interleave :159-213, parallel-tone MSK
+// modulator :228-284) followed by the impairments of SURVEY.md §8(d) (headroom scaling, fractional
+// delay, CFO, AWGN at a per-stream Eb/N0, leading gap), so that tens of GB of distinct per-stream
+// captures can be produced in HBM without host staging.  The modulator's two tone phases advance by
+// exactly -/+ 2*pi/160 per sample, so the waveform is a +/-1-signed lookup in a 160-entry int16
+// table; it differs from opv-mod's output only where opv-mod's accumulated phase rounding flips an
+// int16 truncation (rare, +/-1 LSB).  PARITY captures never come from here: tests run the same bytes
+// through the reference binary.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cmath>
+
+#include "opvd_kernels.cuh"
+
+namespace opvd {
+
+__constant__ int16_t c_tsin[160];
+__constant__ int16_t c_tcos[160];
+__constant__ uint8_t c_lfsr_tx[kFrameBytes];
+
+static bool g_synth_const = false;
+static void upload_synth_constants() {
+    if (g_synth_const) return;
+    int16_t ts[160], tc[160];
+    for (int k = 0; k < 160; ++k) {
+        ts[k] = (int16_t)(16383.0 * std::sin(kTwoPi * k / 160.0));
+        tc[k] = (int16_t)(16383.0 * std::cos(kTwoPi * k / 160.0));
+    }
+    uint8_t lf[kFrameBytes];
+    uint8_t lfsr = 0xFF;  // opv-mod.cpp:97-113
+    for (int i = 0; i < kFrameBytes; ++i) {
+        uint8_t r = 0;
+        for (int b = 7; b >= 0; --b) {
+            r |= (uint8_t)(((lfsr >> 7) & 1) << b);
+            lfsr = (uint8_t)((lfsr << 1) | (((lfsr >> 7) ^ (lfsr >> 6) ^ (lfsr >> 4) ^ (lfsr >> 2)) & 1));
+        }
+        lf[i] = r;
+    }
+    cudaMemcpyToSymbol(c_tsin, ts, sizeof(ts));
+    cudaMemcpyToSymbol(c_tcos, tc, sizeof(tc));
+    cudaMemcpyToSymbol(c_lfsr_tx, lf, sizeof(lf));
+    g_synth_const = true;
+}
+
+__host__ __device__ inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__host__ __device__ inline float u01(uint64_t h) { return (float)((h >> 40) + 1) * (1.0f / 16777217.0f); }
+
+struct StreamImpair {
+    float ebn0_db, cfo_hz, delay;
+    int lead;
+};
+
+__host__ __device__ inline StreamImpair stream_impair(const SynthParams& p, int gstream) {
+    StreamImpair s;
+    const uint64_t h = mix64(p.seed * 0x100000001B3ull + (uint64_t)gstream);
+    s.ebn0_db = p.ebn0_lo_db + (p.ebn0_hi_db - p.ebn0_lo_db) * (float)(gstream % 64) / 63.0f;
+    s.cfo_hz = p.cfo_max_hz * (2.0f * u01(mix64(h + 1)) - 1.0f);
+    s.delay = p.frac_delay ? (float)(mix64(h + 2) >> 40) * (1.0f / 16777216.0f) : 0.0f;
+    s.lead = p.max_lead > 0 ? (int)(mix64(h + 3) % (uint64_t)p.max_lead) : 0;
+    return s;
+}
+
+__host__ __device__ inline void bert_frame(int gstream, uint32_t frame_num, uint8_t* f) {
+    // station id: 48-bit big-endian value (W5NYV's Base-40 code + stream index), token BBAADD, reserved 0
+    const uint64_t id = 0x000003742697ull + (uint64_t)gstream;
+    for (int k = 0; k < 6; ++k) f[k] = (uint8_t)(id >> (40 - 8 * k));
+    f[6] = 0xBB; f[7] = 0xAA; f[8] = 0xDD; f[9] = 0; f[10] = 0; f[11] = 0;
+    for (int i = 0; i < kFrameBytes - 12; ++i) f[12 + i] = (uint8_t)((frame_num + i) & 0xFF);
+}
+
+// one thread per (stream, frame): 2168 tx bits with within-frame differential sign prefix
+__global__ void synth_encode_kernel(SynthParams p, uint8_t* __restrict__ syms, int8_t* __restrict__ fsign) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)p.n_streams * p.n_frames) return;
+    const int stream = (int)(idx / p.n_frames), frame = (int)(idx % p.n_frames);
+    uint8_t pay[kFrameBytes];
+    bert_frame(p.first_stream + stream, (uint32_t)frame, pay);
+    uint8_t* out = syms + ((long long)stream * p.n_frames + frame) * kFrameSymbols;
+    int sign = 1;  // product of d_val over the symbols before this one (within the frame)
+    // sync word, MSB first (opv-mod.cpp:315-321)
+    for (int i = 0; i < kSyncBits; ++i) {
+        const int bit = (kSyncWord >> (kSyncBits - 1 - i)) & 1;
+        out[i] = (uint8_t)(bit | (sign < 0 ? 2 : 0));
+        if (bit) sign = -sign;
+    }
+    // payload: randomise, encode bytes 133..0 MSB first, interleave (opv-mod.cpp:159-213)
+    uint8_t coded[kEncodedBits / 8];  // bit-packed interleaved stream
+    for (int i = 0; i < kEncodedBits / 8; ++i) coded[i] = 0;
+    uint32_t sr = 0;
+    int o = 0;
+    for (int byte_idx = kFrameBytes - 1; byte_idx >= 0; --byte_idx) {
+        const uint8_t byte = pay[byte_idx] ^ c_lfsr_tx[byte_idx];
+        for (int bit_pos = 7; bit_pos >= 0; --bit_pos) {
+            const uint32_t in = (byte >> bit_pos) & 1u;
+            const uint32_t st = (in << 6) | sr;
+            const uint32_t g[2] = {(uint32_t)(__popc(st & 0x4F) & 1), (uint32_t)(__popc(st & 0x6D) & 1)};
+            sr = ((sr << 1) | in) & 0x3F;
+            for (int k = 0; k < 2; ++k, ++o) {
+                const int pos = (o % 32) * 67 + (o / 32);
+                const int corrected = (pos / 8) * 8 + (7 - pos % 8);
+                coded[corrected >> 3] |= (uint8_t)(g[k] << (corrected & 7));
+            }
+        }
+    }
+    for (int i = 0; i < kEncodedBits; ++i) {
+        const int bit = (coded[i >> 3] >> (i & 7)) & 1;
+        out[kSyncBits + i] = (uint8_t)(bit | (sign < 0 ? 2 : 0));
+        if (bit) sign = -sign;
+    }
+    fsign[(long long)stream * p.n_frames + frame] = (int8_t)sign;  // product over the whole frame
+}
+
+// one thread per stream: exclusive prefix product of the per-frame signs
+__global__ void synth_sign_kernel(SynthParams p, int8_t* __restrict__ fsign) {
+    const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+    if (stream >= p.n_streams) return;
+    int8_t* f = fsign + (long long)stream * p.n_frames;
+    int s = 1;
+    for (int k = 0; k < p.n_frames; ++k) {
+        const int pf = f[k];
+        f[k] = (int8_t)s;
+        s *= pf;
+    }
+}
+
+__device__ __forceinline__ float2 clean_sample(const uint8_t* __restrict__ syms, const int8_t* __restrict__ fsign,
+                                               long long k, long long n_sig) {
+    if (k < kSps || k >= n_sig) return make_float2(0.f, 0.f);  // symbol 0 is silent (xor_T starts at 0)
+    const long long m = k / kSps;
+    const int ph = (int)(k % 160);
+    const uint8_t sb = syms[m];
+    int x = fsign[m / kFrameSymbols] * ((sb & 2) ? -1 : 1);
+    float I, Q;
+    if ((sb & 1) == 0) {          // tone F1: phase -2*pi*k/160
+        I = -(float)c_tsin[ph]; Q = (float)c_tcos[ph];
+    } else {                      // tone F2, sign alternates with b_n (opv-mod.cpp:245)
+        if (m & 1) x = -x;
+        I = (float)c_tsin[ph]; Q = (float)c_tcos[ph];
+    }
+    return make_float2(x * I, x * Q);
+}
+
+__global__ void synth_wave_kernel(SynthParams p, uint32_t* __restrict__ iq, const uint8_t* __restrict__ syms,
+                                  const int8_t* __restrict__ fsign) {
+    const int stream = blockIdx.y;
+    const StreamImpair im = stream_impair(p, p.first_stream + stream);
+    const long long n_sig = (long long)p.n_frames * kFrameSymbols * kSps;
+    const uint8_t* ssyms = syms + (long long)stream * p.n_frames * kFrameSymbols;
+    const int8_t* sfs = fsign + (long long)stream * p.n_frames;
+    uint32_t* row = iq + (long long)stream * p.stride;
+    const bool noisy = im.ebn0_db > -100.f;
+    const float amp = 16383.0f * p.scale;
+    const float sigma_c = noisy ? sqrtf(amp * amp * (float)kSps / (0.5f * exp10f(im.ebn0_db / 10.0f)) * 0.5f) : 0.f;
+    const uint64_t skey = mix64(p.seed ^ (0xA5A5A5A5ull + (uint64_t)(p.first_stream + stream) * 0x9E3779B97F4A7C15ull));
+    const double cfo_turns = (double)im.cfo_hz / kSampleRate;
+    for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < p.n_samples;
+         n += (long long)gridDim.x * blockDim.x) {
+        const long long k = n - im.lead;
+        float2 x0 = clean_sample(ssyms, sfs, k, n_sig);
+        if (im.delay != 0.f) {
+            const float2 x1 = clean_sample(ssyms, sfs, k - 1, n_sig);
+            x0.x = (1.f - im.delay) * x0.x + im.delay * x1.x;
+            x0.y = (1.f - im.delay) * x0.y + im.delay * x1.y;
+        }
+        float I = x0.x * p.scale, Q = x0.y * p.scale;
+        if (im.cfo_hz != 0.f) {
+            double t = cfo_turns * (double)n;
+            t -= floor(t);
+            float s, c;
+            sincospif(2.0f * (float)t, &s, &c);
+            const float i2 = I * c - Q * s, q2 = I * s + Q * c;
+            I = i2; Q = q2;
+        }
+        if (noisy) {
+            const uint64_t h = mix64(skey + (uint64_t)n);
+            const float u1 = u01(h), u2 = u01(mix64(h ^ 0xD6E8FEB86659FD93ull));
+            const float rad = sqrtf(-2.0f * __logf(u1)) * sigma_c;
+            float s, c;
+            sincospif(2.0f * u2, &s, &c);
+            I += rad * c; Q += rad * s;
+        }
+        const int iI = max(-32768, min(32767, __float2int_rn(I)));
+        const int iQ = max(-32768, min(32767, __float2int_rn(Q)));
+        row[n] = (uint32_t)(iI & 0xFFFF) | ((uint32_t)(iQ & 0xFFFF) << 16);
+    }
+}
+
+size_t synth_scratch_bytes(const SynthParams& p) {
+    return (size_t)p.n_streams * p.n_frames * (kFrameSymbols + 1) + 256;
+}
+
+void launch_synth(const SynthParams& p, uint32_t* iq, uint8_t* scratch_syms, int8_t* scratch_sign, cudaStream_t st) {
+    upload_synth_constants();
+    const long long nf = (long long)p.n_streams * p.n_frames;
+    if (nf > 0) {
+        synth_encode_kernel<<<(unsigned)((nf + 127) / 128), 128, 0, st>>>(p, scratch_syms, scratch_sign);
+        synth_sign_kernel<<<(p.n_streams + 127) / 128, 128, 0, st>>>(p, scratch_sign);
+    }
+    long long bx = (p.n_samples + 255) / 256;
+    if (bx > 4096) bx = 4096;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)p.n_streams);
+    synth_wave_kernel<<<grid, 256, 0, st>>>(p, iq, scratch_syms, scratch_sign);
+}
+
+// expected-payload check for the synthetic bank: one thread per decoded frame slot
+__global__ void bert_check_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ metrics,
+                                  const FrameRec* __restrict__ frec, const int32_t* __restrict__ n_frames_per_stream,
+                                  int n_streams, int max_frames, SynthParams p, unsigned long long* counters) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_streams * max_frames) return;
+    const int stream = (int)(idx / max_frames), slot = (int)(idx % max_frames);
+    if (slot >= n_frames_per_stream[stream] || metrics[idx] < 0) return;
+    const StreamImpair im = stream_impair(p, p.first_stream + stream);
+    // payload symbol index -> transmitted frame number (nearest)
+    const double sym0 = ((double)frec[idx].payload_start * kSps - im.lead) / kSps - kSyncBits;
+    long long fn = llrint(sym0 / kFrameSymbols);
+    if (fn < 0) fn = 0;
+    uint8_t exp_f[kFrameBytes];
+    bert_frame(p.first_stream + stream, (uint32_t)fn, exp_f);
+    const uint8_t* got = frames + idx * kFrameBytes;
+    unsigned errs = 0;
+    for (int i = 0; i < kFrameBytes; ++i) errs += __popc((unsigned)(exp_f[i] ^ got[i]));
+    atomicAdd(&counters[kCtrBitErrors], (unsigned long long)errs);
+    atomicAdd(&counters[kCtrFramesCompared], 1ull);
+}
+
+void launch_bert_check_impl(const uint8_t* frames, const int32_t* metrics, const FrameRec* frec,
+                            const int32_t* n_frames_per_stream, int n_streams, int max_frames, const SynthParams& p,
+                            unsigned long long* counters, cudaStream_t st) {
+    const long long n = (long long)n_streams * max_frames;
+    if (n <= 0) return;
+    bert_check_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(frames, metrics, frec, n_frames_per_stream,
+                                                                   n_streams, max_frames, p, counters);
+}
+
+}  // namespace opvd

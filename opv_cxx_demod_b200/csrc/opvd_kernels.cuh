@@ -1,0 +1,95 @@
+// opvd_kernels.cuh — launch interface between the host runtime (opvd_api.cu) and the sm_100a
+// kernels (kernels_*.cu).  Everything here is plain device pointers and sizes.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "demod_core.cuh"
+#include "track_core.cuh"
+
+namespace opvd {
+
+// One decoded-frame work item produced by the tracker and consumed by the decoder.
+struct FrameTask {
+    int32_t stream;
+    int32_t slot;           // frame index within the stream (frame_ready order)
+    int64_t payload_start;  // absolute symbol index of the first payload soft symbol
+};
+
+// device-side counters (uint64 each); reduced across ranks by the caller
+enum Counter : int {
+    kCtrSamples = 0,     // samples consumed by the demodulator (call origins advanced + last call)
+    kCtrSymbols,         // soft symbols produced
+    kCtrFramesReady,     // tracker frame_ready events
+    kCtrFramesDecoded,   // metric >= 0
+    kCtrFramesPerfect,   // metric == 0
+    kCtrFramesDropped,   // scale < 1e-10
+    kCtrSyncAcq,         // HUNTING -> VERIFYING
+    kCtrSyncOk,
+    kCtrSyncMiss,
+    kCtrLostLock,
+    kCtrBitErrors,       // vs known BERT payloads (filled by bert_check)
+    kCtrFramesCompared,
+    kCtrAcs,             // Viterbi add-compare-select state updates
+    kNumCounters = 16
+};
+
+struct StreamBuffers {
+    const uint32_t* iq;      // packed int16 I/Q, row-major [stream][stride]
+    int64_t stride;          // samples per row (multiple of 4)
+    const int64_t* avail;    // [S] samples valid in each row (absolute sample count since stream start)
+    int64_t row_base;        // absolute sample index held at row offset 0 (multiple of 64; same for all rows)
+};
+
+struct SoftBuffers {
+    double* soft;            // [stream][stride]
+    int64_t stride;
+    int64_t base;            // absolute symbol index held at row offset 0 (same for all rows)
+};
+
+void launch_estimate(const StreamBuffers& sb, DemodState* dstate, double* est_out, int n_streams, int mode,
+                     int final_flag, cudaStream_t st);
+
+// lanes_per_stream in {1}; returns cudaError
+cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
+                         int mode, int final_flag, double afc_alpha, int lanes_per_stream,
+                         unsigned long long* counters, cudaStream_t st);
+
+void launch_track(const SoftBuffers& so, const DemodState* dstate, TrackState* tstate, int n_streams,
+                  FrameRec* frec, int max_frames, TrackEvent* events, int32_t* n_events, int max_events,
+                  FrameTask* tasks, int32_t* n_tasks, int max_tasks, unsigned long long* counters,
+                  cudaStream_t st);
+
+void launch_decode(const SoftBuffers& so, const FrameTask* tasks, const int32_t* n_tasks_dev, int n_tasks_host,
+                   uint8_t* frames, int32_t* metrics, int max_frames, unsigned long long* counters,
+                   cudaStream_t st);
+
+// stage-level entry (FrameDecoder::decode seam): payloads [n][2144] doubles -> frames [n][134], metrics [n]
+void launch_decode_payloads(const double* payloads, int n, uint8_t* frames, int32_t* metrics,
+                            unsigned long long* counters, cudaStream_t st);
+
+// synthetic OPV bank generator (measurement aid; opv-mod-like TX chain + impairments)
+struct SynthParams {
+    int n_streams;
+    int n_frames;            // frames per stream
+    int64_t stride;          // samples per row
+    int64_t n_samples;       // samples generated per row (lead + n_frames*86720 + tail)
+    uint64_t seed;
+    float scale;             // headroom scaling (0.25)
+    float ebn0_lo_db, ebn0_hi_db;   // per-stream Eb/N0 swept linearly across streams; <= -100 disables noise
+    float cfo_max_hz;        // per-stream CFO uniform in [-cfo_max, +cfo_max]
+    int frac_delay;          // 1: per-stream fractional delay in [0,1)
+    int max_lead;            // per-stream leading gap uniform in [0, max_lead) samples (noise only)
+    int first_stream;        // global index of stream 0 of this rank (seeds are global)
+};
+void launch_synth(const SynthParams& p, uint32_t* iq, uint8_t* scratch_syms, int8_t* scratch_sign,
+                  cudaStream_t st);
+size_t synth_scratch_bytes(const SynthParams& p);
+
+void launch_bert_check_impl(const uint8_t* frames, const int32_t* metrics, const FrameRec* frec,
+                            const int32_t* n_frames_per_stream, int n_streams, int max_frames, const SynthParams& p,
+                            unsigned long long* counters, cudaStream_t st);
+
+void upload_constants();
+
+}  // namespace opvd

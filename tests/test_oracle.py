@@ -1,0 +1,94 @@
+"""CPU tests: the oracle (oracle/opv_oracle.c) against the reference's golden outputs and, when the
+reference build is present (authoring container / shipped oracle/_ref), against the reference itself."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "reference_golden.json")))["cases"]
+STAGE = np.load(os.path.join(HERE, "golden", "stage_vectors.npz"))
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("key", sorted(GOLD))
+def test_oracle_matches_reference_golden(key, cases, ora):
+    name, mode = key.split("/")
+    iq = cases[name]
+    g = GOLD[key]
+    assert _sha(iq) == g["capture_sha256"], "capture generator drifted from the one the golden was made with"
+    r = ora.run(iq, mode == "stream")
+    assert r.frames.shape[0] == g["n_frames"]
+    assert _sha(r.frames) == g["frames_sha256"]                      # stdout bytes of the reference binary
+    assert [[t, i, c] for (t, i, c, _, _) in r.events] == g["events"]  # its stderr transitions
+    assert (0 if r.frames.shape[0] > 0 else 1) == g["exit_code"]
+    assert r.soft.size == g["n_soft"]
+    assert _sha(r.soft) == g["soft_sha256"]                          # soft symbols bit-identical
+    assert r.est_offset == g["est_offset"]
+    assert r.final_freq == g["final_freq"]
+    assert [int(c) for c in r.chunk_starts] == g["chunk_starts"]
+    if g["summary"]:
+        assert g["summary"] == f"Summary: {len(r.frames)} frames ({r.n_perfect} perfect, {len(r.frames) - r.n_perfect} errors)"
+
+
+def test_stage_vectors(ora):
+    for p, f, m in zip(STAGE["payloads"], STAGE["frames"], STAGE["metrics"]):
+        got, metric = ora.frame_decode(p)
+        assert metric == m
+        if m >= 0:
+            assert np.array_equal(got, f)
+    for q, b, m in zip(STAGE["vit_in"], STAGE["vit_bits"], STAGE["vit_metric"]):
+        bits, metric = ora.viterbi_decode(q)
+        assert metric == m and np.array_equal(bits, b)
+
+
+def test_known_answer_constants(ora):
+    # constants derivable from the reference code
+    lf = ora.lfsr_table()
+    assert lf[:16].tolist() == [0xFF, 0x1A, 0xAF, 0x66, 0x52, 0x23, 0x1E, 0x10, 0xA0, 0xF9, 0xFA, 0x8A, 0x98, 0x67, 0x7D, 0xD2]
+    assert lf[-1] == 0x31
+    d = ora.deinterleave_table()
+    assert d[:12].tolist() == [7, 68, 129, 206, 267, 328, 405, 466, 543, 604, 665, 742]
+    assert d[32:36].tolist() == [6, 67, 128, 205]
+    assert sorted(d.tolist()) == list(range(2144))
+    f = ora.bert_frames("W5NYV", 1)[0]
+    assert f[:12].tolist() == [0x00, 0x00, 0x03, 0x74, 0x26, 0x97, 0xBB, 0xAA, 0xDD, 0, 0, 0]
+    assert f[12:].tolist() == [i & 0xFF for i in range(122)]
+
+
+def test_clean_loopback_decodes_bert_payloads(cases, ora):
+    # Makefile:23-33 style loopback: every frame of a clean capture equals its BERT payload
+    for streaming in (False, True):
+        r = ora.run(cases["clean12_call"], streaming)
+        assert np.array_equal(r.frames, ora.bert_frames("KB5MU", 12, first=250))
+        assert r.n_perfect == 12
+        assert r.events[0][:2] == (1, 23) and r.events[1][:2] == (2, 2167)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "opv-demod")),
+                    reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("name", ["clean5", "awgn4", "cfo_m1900", "dropout_long", "zeros_gap", "short_lt_chunk"])
+def test_oracle_vs_reference_live(name, cases, ora):
+    iq = cases[name]
+    for streaming in (False, True):
+        r = ora.run(iq, streaming)
+        fb, evb, rc, _ = ora.run_ref_binary(iq, ["-r"] + (["-s"] if streaming else []))
+        assert np.array_equal(fb, r.frames)
+        assert [(t, i, c) for (t, i, c, _, _) in r.events] == evb
+        soft_ref, est, ff, tf, chunks = ora.ref_run_soft(iq, streaming)
+        assert np.array_equal(soft_ref, r.soft) and est == r.est_offset and ff == r.final_freq
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "opv-mod")),
+                    reason="reference build (oracle/_ref) not present")
+def test_tx_restatement_vs_reference_mod(ora):
+    from tools import captures as cap
+
+    assert np.array_equal(ora.run_ref_mod(["-S", "W5NYV", "-B", "3"]), cap.clean_bert(3))
+    iq, frames = cap.clean_random(2, 5)
+    assert np.array_equal(ora.run_ref_mod(["-R"], stdin=frames.tobytes()), iq)
