@@ -49,7 +49,7 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
 
 // ------------------------------------------------------------------------------------------------
 // A2: estimate.  One CTA per stream, 160 threads = 8 sample-block slots x 20 lag pairs.
-// Lag pair p handles lags p and 40-p (40 products per 40-sample block in total), so the work per
+// Lag pair p handles lags p and 39-p (41 products per 40-sample block in total), so the work per
 // thread is uniform.  Products of int16 and their sums (< 2^47) are exact in FP64, so the
 // reduction order is irrelevant and shared-memory atomics can be used.
 constexpr int kEstThreads = 160;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kEstThreads) est_kernel(StreamBuffers sb, Demo
     const uint32_t* row = sb.iq + (long long)stream * sb.stride - row0;
     const int n_blocks = (int)(n_use / kSps);
     const int slot = threadIdx.x / 20, pair = threadIdx.x % 20;
-    const int lagA = pair, lagB = kSps - pair;  // lagB == 40 for pair 0 -> no terms
+    const int lagA = pair, lagB = kSps - 1 - pair;  // lags 0..19 and 39..20: 41 products per block for every pair
     double arA = 0, aiA = 0, arB = 0, aiB = 0;
 
     for (int blk0 = 0; blk0 < n_blocks; blk0 += kEstTile) {

@@ -1,0 +1,268 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI / the drop-in CLI,
+against the oracle (oracle/opv_oracle.c, pinned to the reference) and, when shipped, the reference
+binary itself (oracle/_ref/opv-demod) on the same bytes.
+
+Bars: frames, sync events/indices, exit codes: bit-exact.  Soft symbols: north_star allows 1e-4
+relative; the FP64 kernels are held to 1e-9 of the stream's rms.
+"""
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "reference_golden.json")))["cases"]
+STAGE = np.load(os.path.join(HERE, "golden", "stage_vectors.npz"))
+SOFT_TOL = 1e-9
+
+NAMES = ["clean5", "clean12_call", "awgn14", "awgn8", "awgn4", "cfo_p1200_delay", "cfo_m1900", "random6",
+         "dropout_short", "dropout_long", "zeros_gap", "noise_only", "short_lt_chunk", "tiny", "empty"]
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import torch
+
+    assert torch.cuda.is_available()
+    import opv_cxx_demod_b200 as p
+
+    assert os.path.exists(p.LIB_PATH), "libopvd.so must be built in-tree (no fallback exists)"
+    return p
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _soft_err(got, ref):
+    if ref.size == 0:
+        return 0.0
+    return float(np.max(np.abs(got - ref)) / (np.sqrt(np.mean(ref ** 2)) + 1e-300))
+
+
+def _run_bank(pkg, caps, streaming, **kw):
+    n = max(max(c.shape[0] for c in caps), 64)
+    bank = pkg.DemodBank(len(caps), streaming=streaming, max_samples=n, **kw)
+    for s, c in enumerate(caps):
+        if c.shape[0]:
+            bank.push_iq(s, c)
+    bank.run(final=True)
+    return bank
+
+
+@pytest.mark.parametrize("streaming", [False, True])
+def test_all_cases_one_bank_vs_oracle_and_golden(streaming, pkg, cases, ora):
+    """All standard captures as ONE ragged multi-stream bank: frames / events / soft / offsets per stream."""
+    caps = [cases[n] for n in NAMES]
+    bank = _run_bank(pkg, caps, streaming)
+    fr = bank.poll_frames()
+    problems = []
+    for s, name in enumerate(NAMES):
+        ref = ora.run(caps[s], streaming)
+        g = GOLD[f"{name}/{'stream' if streaming else 'batch'}"]
+        got = fr.of_stream(s)
+        ev = bank.poll_events(s)
+        info = bank.stream_info(s)
+        soft = bank.get_soft(s)
+        checks = {
+            "n_frames": got.shape[0] == g["n_frames"],
+            "frames_sha_vs_reference_stdout": _sha(got) == g["frames_sha256"],
+            "frames_vs_oracle": np.array_equal(got, ref.frames),
+            "metrics": np.array_equal(fr.metric[fr.stream == s], ref.metrics),
+            "ready_idx": np.array_equal(fr.ready_idx[fr.stream == s], ref.frame_ready_idx),
+            "events": [[t, i, c] for (t, i, c, _, _) in ev] == g["events"],
+            "n_symbols": info["n_symbols"] == g["n_soft"],
+            "est_offset": info["est_offset_hz"] == g["est_offset"],
+            "final_freq": abs(info["freq_offset_hz"] - g["final_freq"]) < 1e-6,
+            "sync_state": info["sync_state"] == ref.final_state,
+            "soft": soft.size == ref.soft.size and _soft_err(soft, ref.soft) < SOFT_TOL,
+            "event_corr": all(abs(a[3] - b[3]) < 1e-9 and abs(a[4] - b[4]) <= 1e-9 * max(1.0, abs(b[4]))
+                              for a, b in zip(ev, ref.events)),
+        }
+        bad = [k for k, ok in checks.items() if not ok]
+        if bad:
+            problems.append((name, bad, info["est_offset_hz"], g["est_offset"],
+                             _soft_err(soft, ref.soft) if soft.size == ref.soft.size else None))
+    assert not problems, problems
+    c = bank.counters()
+    assert c["frames_decoded"] == fr.data.shape[0]
+    assert c["symbols"] == sum(GOLD[f"{n}/{'stream' if streaming else 'batch'}"]["n_soft"] for n in NAMES)
+    bank.close()
+
+
+def test_stage_decode_vs_reference_vectors(pkg):
+    """FrameDecoder::decode seam on vectors produced by the reference's own decoder (incl. ties and drops)."""
+    frames, metrics = pkg.stage_decode(STAGE["payloads"])
+    assert metrics.tolist() == STAGE["metrics"].tolist()
+    ok = STAGE["metrics"] >= 0
+    assert np.array_equal(frames[ok], STAGE["frames"][ok])
+
+
+def test_stage_decode_random_vs_oracle(pkg, ora):
+    rng = np.random.default_rng(5)
+    p = rng.normal(0, 1, (300, 2144)) * rng.uniform(1e3, 1e12, (300, 1))
+    p[::7] = np.round(p[::7] / np.abs(p[::7]).mean(axis=1, keepdims=True) * 2) * 1e5  # coarse levels: quantiser edges + ties
+    frames, metrics = pkg.stage_decode(p)
+    for i in range(p.shape[0]):
+        f, m = ora.frame_decode(p[i])
+        assert m == metrics[i], i
+        assert np.array_equal(f, frames[i]), i
+
+
+def test_streaming_push_granularity_invariance(pkg, cases, ora):
+    """Stream mode: the chunk schedule depends on sample counts only, not on how the bytes arrive."""
+    iq = cases["cfo_p1200_delay"]
+    ref = ora.run(iq, True)
+    rng = np.random.default_rng(3)
+    bank = pkg.DemodBank(1, streaming=True, max_samples=iq.shape[0])
+    pos = 0
+    frames = []
+    while pos < iq.shape[0]:
+        n = int(rng.integers(1, 150000))
+        bank.push_iq(0, iq[pos:pos + n])
+        pos += n
+        bank.run(final=False)
+        frames.append(bank.poll_frames().data)
+    bank.run(final=True)
+    frames.append(bank.poll_frames().data)
+    assert np.array_equal(np.concatenate(frames), ref.frames)
+    assert _soft_err(bank.get_soft(0), ref.soft) < SOFT_TOL
+    assert [(t, i, c) for (t, i, c, _, _) in bank.poll_events(0)] == [(t, i, c) for (t, i, c, _, _) in ref.events]
+    bank.close()
+
+
+def test_streaming_unbounded_input_compaction(pkg, ora):
+    """A long stream through a small library-owned buffer (front compaction of samples and soft symbols)."""
+    from tools import captures as cap
+
+    iq = cap.impair(cap.clean_bert(30), 77, ebn0_db=13.0, cfo_hz=-300.0, lead_gap=1234)
+    ref = ora.run(iq, True)
+    bank = pkg.DemodBank(1, streaming=True, max_samples=4 * 86720, max_frames=16)
+    frames = []
+    for pos in range(0, iq.shape[0], 100000):
+        bank.push_iq(0, iq[pos:pos + 100000])
+        bank.run(final=False)
+        frames.append(bank.poll_frames().data)
+    bank.run(final=True)
+    frames.append(bank.poll_frames().data)
+    assert np.array_equal(np.concatenate(frames), ref.frames)
+    bank.close()
+
+
+def test_init_offset_and_alpha_flags(pkg, cases, ora):
+    iq = cases["cfo_m1900"]
+    for kw in (dict(init_offset=-700.0), dict(afc_alpha=0.004), dict(init_offset=250.0, afc_alpha=0.0005)):
+        ref = ora.run(iq, True, afc_alpha=kw.get("afc_alpha", 0.001), init_offset=kw.get("init_offset"))
+        bank = pkg.DemodBank(1, streaming=True, max_samples=iq.shape[0], afc_alpha=kw.get("afc_alpha", 0.001),
+                             init_offset_hz=kw.get("init_offset"))
+        bank.push_iq(0, iq)
+        bank.run(final=True)
+        assert np.array_equal(bank.poll_frames().data, ref.frames), kw
+        assert _soft_err(bank.get_soft(0), ref.soft) < SOFT_TOL, kw
+        bank.close()
+    # -o is ignored in batch mode (src/opv-demod.cpp:1164-1167)
+    ref = ora.run(iq, False)
+    bank = pkg.DemodBank(1, streaming=False, max_samples=iq.shape[0], init_offset_hz=-700.0)
+    bank.push_iq(0, iq)
+    bank.run(final=True)
+    assert bank.stream_info(0)["est_offset_hz"] == ref.est_offset
+    assert np.array_equal(bank.poll_frames().data, ref.frames)
+    bank.close()
+
+
+@pytest.mark.parametrize("name", ["clean5", "awgn8", "dropout_long", "zeros_gap", "short_lt_chunk", "empty"])
+@pytest.mark.parametrize("flags", [["-r", "-q"], ["-s", "-r", "-q"], ["-s", "-r"], ["-r"]])
+def test_cli_dropin_vs_reference_process(name, flags, pkg, cases, ora):
+    """The drop-in executable against the reference process on the same stdin bytes:
+    stdout bytes, exit code, tracker lines and Summary line."""
+    iq = cases[name]
+    mine = subprocess.run([pkg.CLI_PATH, *flags], input=np.ascontiguousarray(iq).tobytes(), capture_output=True)
+    g = GOLD[f"{name}/{'stream' if '-s' in flags else 'batch'}"]
+    assert mine.returncode == g["exit_code"], mine.stderr.decode("utf8", "replace")[-400:]
+    assert hashlib.sha256(mine.stdout).hexdigest() == g["frames_sha256"]
+    err = mine.stderr.decode("utf-8", "replace")
+    assert [[t, i, c] for (t, i, c) in ora.parse_events(err)] == g["events"]
+    if "-q" not in flags and g["summary"]:
+        assert g["summary"] in err
+    if ora.have_ref():
+        ref = subprocess.run([ora.REF_DEMOD, *flags], input=np.ascontiguousarray(iq).tobytes(), capture_output=True)
+        assert ref.stdout == mine.stdout and ref.returncode == mine.returncode
+        rerr = ref.stderr.decode("utf-8", "replace")
+        # identical human-readable stderr apart from float formatting of soft-derived values
+        keep = lambda t: [l for l in t.splitlines() if l.startswith(("Summary", "Final state", "Total", "Estimated", "Loaded", "Demodulated", "│ Station", "│ Token", "│ FRAME"))]
+        assert keep(rerr) == keep(err)
+
+
+def test_synth_bank_matches_tx_restatement(pkg, ora):
+    """The device generator without impairments reproduces opv-mod's waveform (apart from rare +/-1 LSB
+    truncation flips caused by opv-mod's accumulated phase rounding) and decodes to its BERT payloads."""
+    import torch
+
+    n_frames, S = 3, 4
+    n = n_frames * 86720 + 4000
+    stride = (n + 63) // 64 * 64
+    buf = torch.zeros((S, stride), dtype=torch.int32, device="cuda")
+    sp = pkg.make_synth(S, n_frames, stride, n, seed=9, scale=1.0)
+    pkg.synth_bank(buf.data_ptr(), sp)
+    got = buf.cpu().numpy().view(np.int16).reshape(S, stride, 2)[:, :n]
+    for s in range(S):
+        want_frames = np.zeros((n_frames, 134), np.uint8)
+        for k in range(n_frames):
+            want_frames[k, :6] = list((0x000003742697 + s).to_bytes(6, "big"))
+            want_frames[k, 6:9] = [0xBB, 0xAA, 0xDD]
+            want_frames[k, 12:] = [(k + i) & 0xFF for i in range(122)]
+        want = ora.modulate(want_frames)
+        d = np.abs(got[s].astype(np.int32) - want.astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3
+    bank = pkg.DemodBank(S, streaming=True)
+    bank.attach_device_iq(buf.data_ptr(), stride, n, keepalive=buf)
+    bank.run(final=True)
+    fr = bank.poll_frames()
+    assert fr.data.shape[0] == S * n_frames and (fr.metric == 0).all()
+    bank.bert_check(sp)
+    c = bank.counters()
+    assert c["frames_compared"] == S * n_frames and c["bit_errors"] == 0
+    bank.close()
+
+
+def test_resident_bank_properties_and_reference_spotcheck(pkg, ora):
+    """A resident impaired bank (device generator): size-independent properties on every stream and
+    bit-exact frames against the oracle on a sample of streams copied back to the host."""
+    import torch
+
+    S, n_frames = 96, 6
+    n = n_frames * 86720 + 20000
+    stride = (n + 63) // 64 * 64
+    buf = torch.zeros((S, stride), dtype=torch.int32, device="cuda")
+    sp = pkg.make_synth(S, n_frames, stride, n, seed=4, ebn0_lo_db=2.0, ebn0_hi_db=16.0, cfo_max_hz=1500.0,
+                        frac_delay=True, max_lead=15000)
+    pkg.synth_bank(buf.data_ptr(), sp)
+    for streaming in (True, False):
+        bank = pkg.DemodBank(S, streaming=streaming)
+        bank.attach_device_iq(buf.data_ptr(), stride, n, keepalive=buf)
+        bank.run(final=True)
+        fr = bank.poll_frames()
+        c = bank.counters()
+        assert c["samples"] == S * n
+        assert c["frames_decoded"] == fr.data.shape[0] <= S * n_frames
+        assert c["frames_ready"] == c["frames_decoded"] + c["frames_dropped"]
+        host = buf.cpu().numpy().view(np.int16).reshape(S, stride, 2)[:, :n]
+        for s in list(range(0, S, 7)):
+            ref = ora.run(host[s], streaming)
+            assert np.array_equal(fr.of_stream(s), ref.frames), (s, streaming)
+            assert _soft_err(bank.get_soft(s), ref.soft) < SOFT_TOL
+            assert [(t, i, c2) for (t, i, c2, _, _) in bank.poll_events(s)] == [(t, i, c2) for (t, i, c2, _, _) in ref.events]
+        bank.close()
+    # high-SNR streams must decode their known BERT payloads
+    bank = pkg.DemodBank(S, streaming=True)
+    bank.attach_device_iq(buf.data_ptr(), stride, n, keepalive=buf)
+    bank.run(final=True)
+    bank.bert_check(sp)
+    c = bank.counters()
+    assert c["frames_compared"] == c["frames_decoded"]
+    bank.close()

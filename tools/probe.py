@@ -1,0 +1,31 @@
+"""Quick throughput probe on a resident synthetic bank (development aid; bench.py is the contract)."""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import opv_cxx_demod_b200 as pkg
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--streams", type=int, default=1024)
+ap.add_argument("--frames", type=int, default=25)
+ap.add_argument("--mode", default="stream")
+ap.add_argument("--lanes", type=int, default=0)
+ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--ebn0", type=float, nargs=2, default=[2.0, 10.0])
+a = ap.parse_args()
+S, nf = a.streams, a.frames
+n = nf * 86720 + 8000
+stride = (n + 63) // 64 * 64
+buf = torch.empty((S, stride), dtype=torch.int32, device="cuda")
+sp = pkg.make_synth(S, nf, stride, n, seed=1, ebn0_lo_db=a.ebn0[0], ebn0_hi_db=a.ebn0[1], cfo_max_hz=0.0, max_lead=4000)
+t0 = time.time(); pkg.synth_bank(buf.data_ptr(), sp); torch.cuda.synchronize(); t1 = time.time()
+print(f"synth {S}x{n} samples ({S*n*4/1e9:.2f} GB) in {t1-t0:.2f}s", flush=True)
+for rep in range(a.reps):
+    bank = pkg.DemodBank(S, streaming=(a.mode == "stream"), lanes_per_stream=a.lanes)
+    bank.attach_device_iq(buf.data_ptr(), stride, n, keepalive=buf)
+    t0 = time.time(); bank.run(final=True); t1 = time.time()
+    ms = bank.last_run_ms(); c = bank.counters()
+    tot = ms["total"] / 1e3
+    print(json.dumps({"rep": rep, "S": S, "frames": nf, "ms": ms, "wall_s": round(t1 - t0, 4),
+                      "Msps": round(S * n / tot / 1e6, 1), "GBps": round(S * n * 4 / tot / 1e9, 1),
+                      "frames_per_s": round(c["frames_decoded"] / tot, 1), "counters": c}), flush=True)
+    bank.close()
