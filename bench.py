@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native opv-demod receive chain.
+
+Metric (BASELINE.json): aggregate demod Msamples/s (and decoded frames/s) over N B200s, against
+the HBM roofline of the front-end kernel, with the reference's CPU opv-demod timed beside it.
+
+Workload at N=1 = BASELINE.json configs[1]: 1,024 streams x 10 s (250 frames, 21.68 M samples,
+86.7 MB each; 88.8 GB resident) of synthetic opv-mod-like captures with AWGN, Eb/N0 swept
+2..10 dB across streams.  N>1: every rank owns its own 1,024 streams ("scaling": "weak"; the
+16,384-stream bank of configs[4] is `--streams 16384 --seconds 1`).  A step = one pass of the
+whole chain (estimate -> demod -> sync tracker -> Viterbi) over the rank's bank in streaming mode
+(`opv-demod -s` semantics), from fresh per-stream state.
+
+  value   device-timed (CUDA events on the library's stream), inputs resident in HBM
+  e2e     same chain through the C ABI from pinned HOST buffers: H2D of the samples, run, D2H of
+          the decoded frames, on a bounded duration of the same streams (rate metric)
+  --impl reference   the reference's own CPU opv-demod (oracle/_ref), one process per host core
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = 2168000.0
+FRAME_SAMPLES = 86720
+METRIC = "aggregate_demod_msps"
+UNIT = "Msamples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=1024, help="streams per GPU")
+    ap.add_argument("--seconds", type=float, default=10.0, help="capture length per stream")
+    ap.add_argument("--lanes", type=int, default=0, help="GPU lanes per stream (0 = automatic)")
+    ap.add_argument("--e2e-seconds", type=float, default=0.52, help="capture length per stream for the e2e leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(streams, seconds):
+    return f"{streams} streams x {seconds:g} s synthetic opv-mod captures, AWGN Eb/N0 2-10 dB (BASELINE configs[1] shape)"
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_profile_json(name):
+    p = os.path.join(ROOT, "profiles", name)
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(captures, threads):
+    """Time the reference's CPU opv-demod (-s -r -q), one process per capture, all started together.
+    captures: list of int16 [n,2] arrays.  Returns (wall_s, total_samples, total_frames, outputs)."""
+    from oracle import oracle as ora
+
+    binary = ora.REF_DEMOD if os.path.exists(ora.REF_DEMOD) else None
+    tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    files = []
+    for k, c in enumerate(captures):
+        f = os.path.join(tmp, f"opvd_bench_{os.getpid()}_{k}.iq")
+        c.tofile(f)
+        files.append(f)
+    outs = []
+    try:
+        if binary:
+            t0 = time.perf_counter()
+            procs = [subprocess.Popen([binary, "-s", "-r", "-q"], stdin=open(f, "rb"), stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL) for f in files]
+            outs = [p.communicate()[0] for p in procs]
+            wall = time.perf_counter() - t0
+            kind = "reference"
+        else:  # the oracle port (single C restatement per capture, threads via processes is not available)
+            import numpy as np
+
+            t0 = time.perf_counter()
+            outs = [ora.run(c, True, want_soft=False).frames.tobytes() for c in captures]
+            wall = time.perf_counter() - t0
+            kind, threads = "port", 1
+    finally:
+        for f in files:
+            try:
+                os.remove(f)
+            except OSError:
+                pass
+    samples = sum(int(c.shape[0]) for c in captures)
+    frames = sum(len(o) // 134 for o in outs)
+    return wall, samples, frames, outs, kind, threads
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation on all host cores, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+
+    from tools import captures as cap
+
+    cores = os.cpu_count() or 1
+    frames_per_proc = 40  # ~3.5 M samples, ~0.5 s of CPU per process and step
+    base = cap.clean_bert(frames_per_proc)
+    caps = [cap.impair(base, 1000 + k, ebn0_db=2.0 + 8.0 * (k % 64) / 63.0, lead_gap=(k * 997) % 4000) for k in range(cores)]
+    times, samples, frames = [], 0, 0
+    kind = "reference"
+    for it in range(args.warmup + args.steps):
+        wall, s, f, _, kind, thr = cpu_reference_run(caps, cores)
+        if it >= args.warmup:
+            times.append(wall)
+            samples += s
+            frames += f
+    total = sum(times)
+    value = samples / total / 1e6
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / max(len(times), 1), 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.streams, args.seconds),
+                   "sample": f"{cores} streams x {frames_per_proc} frames per step, one opv-demod -s -r -q process per core"},
+        "frames_per_s": round(frames / total, 2),
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{cores} x {frames_per_proc}-frame captures per step"},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import opv_cxx_demod_b200 as pkg
+    from opv_cxx_demod_b200.shard import reduce_counters, reduce_max_ms, stream_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the opv-demod CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S = args.streams                      # per rank (weak scaling)
+    lo, hi = stream_range(rank, world, S * world)
+    n_frames = int(round(args.seconds * FS / FRAME_SAMPLES))
+    max_lead = 4000
+    n = n_frames * FRAME_SAMPLES + max_lead + 4000
+    stride = (n + 63) // 64 * 64
+
+    # ---- synthetic bank, resident in HBM (outside every timed region)
+    bank_buf = torch.empty((S, stride), dtype=torch.int32, device=dev)
+    sp = pkg.make_synth(S, n_frames, stride, n, seed=20261017, ebn0_lo_db=2.0, ebn0_hi_db=10.0, max_lead=max_lead,
+                        first_stream=lo)
+    pkg.synth_bank(bank_buf.data_ptr(), sp, device=local_rank)
+    bank = pkg.DemodBank(S, streaming=True, device=local_rank, lanes_per_stream=args.lanes)
+    bank.attach_device_iq(bank_buf.data_ptr(), stride, n, keepalive=bank_buf)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        bank.reset()
+        bank.run(final=True, sync=True)
+        return bank.last_run_ms()
+
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    per_kernel = {"estimate": 0.0, "demod": 0.0, "track": 0.0, "decode": 0.0, "total": 0.0}
+    for _ in range(args.steps):
+        ms = one_step()
+        for k in per_kernel:
+            per_kernel[k] += ms[k]
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    clocks = sampler.stop()
+    counters = bank.counters()            # of the last step
+    bank.bert_check(sp)
+    ber = bank.counters()
+
+    dev_ms = reduce_max_ms(per_kernel["total"], dev)          # max over ranks of the device-timed K steps
+    tot = reduce_counters({k: counters[k] for k in ("samples", "symbols", "frames_decoded", "frames_ready",
+                                                    "sync_acq", "sync_miss", "lost_lock", "acs")}
+                          | {"bit_errors": ber["bit_errors"], "frames_compared": ber["frames_compared"]}, dev)
+    value = tot["samples"] * args.steps / (dev_ms * 1e-3) / 1e6
+    frames_per_s = tot["frames_decoded"] * args.steps / (dev_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (demod): algorithmic bytes = 4 B/sample (+134 B/frame, negligible)
+    peak, peak_src = measured_peaks()
+    demod_ms = per_kernel["demod"] / args.steps
+    ach = counters["samples"] * 4 / (demod_ms * 1e-3) / 1e9
+    traffic = load_profile_json("roofline_traffic.json")
+    mb = load_profile_json("microbench_r01.json")
+    roofline = {"bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
+                "traffic": (traffic or {}).get("demod_kernel_dram_bytes_per_sample"),
+                "kernel": "demod_kernel", "launch_ms": round(demod_ms, 3), "peak_source": peak_src,
+                "note": "FP64-pipe bound (reference arithmetic is FP64); see fp64"}
+    fp64_ops_per_sample = 24.0  # FP64 instructions per sample of the restructured correlator
+    if mb:
+        roofline["fp64"] = {"achieved_dfma_per_s": round(counters["samples"] * fp64_ops_per_sample / (demod_ms * 1e-3), 1),
+                            "peak_dfma_per_s": mb["dfma_per_s"],
+                            "frac": round(counters["samples"] * fp64_ops_per_sample / (demod_ms * 1e-3) / mb["dfma_per_s"], 4)}
+    viterbi = {"acs_per_s": round(counters["acs"] / max(per_kernel["decode"] / args.steps * 1e-3, 1e-9), 1),
+               "decode_ms": round(per_kernel["decode"] / args.steps, 3)}
+    if mb:
+        viterbi["dpx_peak_ops_per_s"] = mb["dpx_vibmin_add_per_s"]
+        viterbi["frac_of_dpx_peak"] = round(viterbi["acs_per_s"] / 2.0 / mb["dpx_vibmin_add_per_s"], 4)  # 2 states per DPX op
+
+    # ---- e2e: host buffers through the C ABI (H2D + run + D2H of frames), bounded duration
+    e2e = None
+    if not args.no_e2e:
+        nf_e = max(2, int(round(args.e2e_seconds * FS / FRAME_SAMPLES)))
+        n_e = nf_e * FRAME_SAMPLES + max_lead
+        host = torch.empty((S, n_e), dtype=torch.int32, pin_memory=True)
+        host.copy_(bank_buf[:, :n_e])
+        torch.cuda.synchronize()
+        ebank = pkg.DemodBank(S, streaming=True, device=local_rank, max_samples=n_e, lanes_per_stream=args.lanes)
+        d2h = 0
+
+        def e2e_step():
+            ebank.reset()
+            ebank.push_iq_host_ptr(host.data_ptr(), n_e, n_e)
+            ebank.run(final=True, sync=False)
+            fr = ebank.poll_frames()
+            return fr
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fr = e2e_step()
+            d2h = int(fr.data.nbytes + fr.metric.nbytes + fr.payload_start.nbytes)
+        barrier()
+        e_s = time.perf_counter() - t0
+        e_s = reduce_max_ms(e_s, dev)
+        e_val = S * world * n_e * args.steps / e_s / 1e6
+        e2e = {"value": round(e_val, 2), "unit": UNIT, "h2d_bytes_per_step": int(S * n_e * 4), "d2h_bytes_per_step": d2h,
+               "sample": f"{S} streams x {nf_e} frames ({n_e} samples) per rank per step from pinned host memory",
+               "frames_per_step": int(fr.data.shape[0])}
+        ebank.close()
+        del host
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference binary, one process per core
+    cpu_baseline, spot = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        fpp = 60
+        n_c = fpp * FRAME_SAMPLES
+        hostc = bank_buf[:cores, :n_c].cpu().numpy().view(np.int16).reshape(cores, n_c, 2)
+        caps = [np.ascontiguousarray(hostc[k]) for k in range(cores)]
+        wall, s_c, f_c, outs, kind, thr = cpu_reference_run(caps, cores)
+        cpu_baseline = {"value": round(s_c / wall / 1e6, 3), "unit": UNIT, "cores": thr, "kind": kind,
+                        "frames_per_s": round(f_c / wall, 2),
+                        "sample": f"first {fpp} frames of streams 0..{cores - 1} of the same bank, one opv-demod -s -r -q per core"}
+        # parity spot check on the same bytes: the reference's frames are a prefix of the GPU's (causal chain)
+        fr = bank.poll_frames()
+        mism, compared = 0, 0
+        for k, o in enumerate(outs):
+            ref = np.frombuffer(o, np.uint8).reshape(-1, 134)
+            got = fr.of_stream(k)
+            m = max(ref.shape[0] - 1, 0)
+            compared += m
+            mism += int((ref[:m] != got[:m]).any(axis=1).sum()) if got.shape[0] >= m else m
+        spot = {"streams": cores, "frames_compared": compared, "frame_mismatches": mism}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(S, args.seconds), "streams_per_gpu": S, "streams_total": S * world,
+                       "frames_per_stream": n_frames, "samples_per_stream": n, "mode": "stream (-s)",
+                       "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2; no flush needed" % (S * n * 4 / 1e9),
+                       "lanes_per_stream": args.lanes},
+            "frames_per_s": round(frames_per_s, 1),
+            "wall_ms_per_step": round(wall_ms / args.steps, 3),
+            "kernel_ms_per_step": {k: round(v / args.steps, 3) for k, v in per_kernel.items()},
+            "counters": tot,
+            "ber": (tot["bit_errors"] / (tot["frames_compared"] * 1072.0)) if tot["frames_compared"] else None,
+            "roofline": roofline, "viterbi": viterbi, "cpu_baseline": cpu_baseline, "parity_spotcheck": spot,
+            "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    bank.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

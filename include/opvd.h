@@ -94,6 +94,9 @@ enum { OPVD_CTR_SAMPLES = 0, OPVD_CTR_SYMBOLS, OPVD_CTR_FRAMES_READY, OPVD_CTR_F
  *      one set per stream. */
 int opvd_create(const opvd_config* cfg, opvd_handle** out);
 int opvd_destroy(opvd_handle* h);
+/* back to the state right after opvd_create (fresh demod/tracker/decoder objects, counters zero); buffers and an
+ * attached capture are kept.  Lets a benchmark repeat the same pass without reallocating. */
+int opvd_reset(opvd_handle* h);
 const char* opvd_strerror(int code);
 const char* opvd_last_cuda_error(const opvd_handle* h);
 int opvd_version(void);

@@ -26,7 +26,7 @@ COUNTER_NAMES = ["samples", "symbols", "frames_ready", "frames_decoded", "frames
                  "sync_acq", "sync_ok", "sync_miss", "lost_lock", "bit_errors", "frames_compared", "acs"]
 
 # every symbol include/opvd.h declares (checked by tests/test_abi.py)
-EXPORTS = ["opvd_create", "opvd_destroy", "opvd_strerror", "opvd_last_cuda_error", "opvd_version",
+EXPORTS = ["opvd_create", "opvd_destroy", "opvd_reset", "opvd_strerror", "opvd_last_cuda_error", "opvd_version",
            "opvd_push_iq", "opvd_push_iq_all", "opvd_attach_device_iq", "opvd_run", "opvd_sync",
            "opvd_poll_frames", "opvd_poll_events", "opvd_get_soft", "opvd_get_stream_info",
            "opvd_get_counters", "opvd_counters_device_ptr", "opvd_last_run_ms", "opvd_stage_decode",
@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
     H = C.c_void_p
     L.opvd_create.argtypes = [C.POINTER(Config), C.POINTER(H)]
     L.opvd_destroy.argtypes = [H]
+    L.opvd_reset.argtypes = [H]
     L.opvd_strerror.restype = C.c_char_p
     L.opvd_strerror.argtypes = [C.c_int]
     L.opvd_last_cuda_error.restype = C.c_char_p

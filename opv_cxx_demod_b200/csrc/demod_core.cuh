@@ -1,8 +1,7 @@
 // demod_core.cuh — per-symbol arithmetic of the dual-tone MSK demodulator with AFC and
 // early-late symbol timing recovery (reference: MSKDemodulatorAFC::demodulate,
-// /root/reference/src/opv-demod.cpp:206-329), restructured for one-stream-per-lane execution
-// on B200's FP64 pipe.  Host/device code: the CUDA kernels and the CPU host-sim test compile
-// exactly this arithmetic.
+// /root/reference/src/opv-demod.cpp:206-329), restructured for B200's FP64 pipe.
+// Host/device code: the CUDA kernels and the CPU host-sim test compile exactly this arithmetic.
 //
 // What the reference computes per symbol (position pos = b + f, b integer, 0 <= f < 1):
 //     corr_t   = sum_{i<40} y[i]    * exp(-j(ph_t + i*inc_t))        on-time, tone t in {1,2}
@@ -12,7 +11,7 @@
 // at a cost of 3 interpolations, 4 libm trig calls and 6 complex MACs per sample.  Only
 // |corr|^2, |early|^2, |late|^2 and arg(corr_n * conj(corr_{n-1})) are ever used (:264-306).
 //
-// Restructuring (exact in real arithmetic, ~1e-15 relative in FP64):
+// Restructuring (exact in real arithmetic, ~1e-12 of rms in FP64 after the loops have fed back):
 //  * z = exp(-j*inc_t).  All three gates are polynomials in z over the SAME 61 raw samples
 //    s[b-10 .. b+50]; the common factor exp(-j*ph_t) has modulus 1 and drops out of the norms.
 //  * Each polynomial is evaluated by Horner over 12 segments of 5 samples (4 FMAs per sample and
@@ -22,6 +21,9 @@
 //        dX = -s[first] + s[last+1]*z^40
 //  * AFC needs corr_n*conj(corr_{n-1}); the phase advance between two symbol starts is 40*inc_t
 //    of the earlier symbol, so the previous on-time sum is stored pre-rotated by conj(z^40).
+//  * The tone steps are exactly -/+ 2*pi/160 plus the AFC term delta = 2*pi*offset/fs with
+//    |delta| <= 0.006, so z_t = tau^(+/-1) * zeta with tau a constant and zeta = exp(-j*delta)
+//    from a short Taylor polynomial: no sincos call on the per-symbol critical path.
 //  * The absolute LO phases are still tracked (2 FMAs per symbol) because the reference's
 //    atan2 sees signed zeros when a correlation is exactly 0 (all-zero input, e.g. the 4000
 //    trailing zeros opv-mod appends): the +/-pi it then returns depends on the quadrant of the
@@ -43,7 +45,7 @@ struct DemodState {
     int64_t call_len;     // N of the open call (0 = none open)
     int64_t n_sym;        // soft symbols produced so far (global symbol index of the next one)
     int32_t sym_in_call;  // symbols produced in the open call; 0 => AFC update skipped (:289)
-    int32_t flags;        // kFlagDone | kFlagEstDone
+    int32_t flags;        // kFlagDone | kFlagEstDone | kFlagFlush
 };
 constexpr int32_t kFlagDone = 1;     // EOF flush performed (stream mode) / single call finished (batch)
 constexpr int32_t kFlagEstDone = 2;  // initial offset decided (estimate, -o, or "never" for short streams)
@@ -56,28 +58,67 @@ OPVD_HD void demod_state_init(DemodState& s) {
     s.origin = 0; s.call_len = 0; s.n_sym = 0; s.sym_in_call = 0; s.flags = 0;
 }
 
-// e^{-j*inc} for both tones from the current AFC offset (:210-211, :305-306)
+// ---------------------------------------------------------------------------------------------
+// LO steps.  inc_t = 2*pi*(-/+13550 + offset)/fs (:210-211, :305-306); 13550/fs = 1/160 exactly.
+constexpr double kTauC = 0.9992290362407229;         // cos(2*pi/160)
+constexpr double kTauS = 0.03925981575906861;        // sin(2*pi/160)
+constexpr double kIncDev = 0.039269908169872414;     // 2*pi/160
+constexpr double kTwoPiOverFs = 2.8981482044186284e-06;
+constexpr double kSymRateOverTwoPi = 8626.197915580728;  // 54200 / (2*pi)  (:300)
+constexpr double kInvTwoPi = 0.15915494309189535;
+
+// zeta = exp(-j*delta), delta = 2*pi*offset/fs.  Taylor to delta^12: exact to < 1e-17 for
+// |offset| <= 50 kHz (the AFC clamps to +/-2 kHz, :303; a larger -o value is possible before the
+// first update), sincos() beyond that.
+OPVD_HD cplx zeta_from_offset(double offset_hz, double& delta) {
+    const double d = offset_hz * kTwoPiOverFs;
+    delta = d;
+    if (fabs(d) > 0.145) {
+        double s, c;
+        sincos(d, &s, &c);
+        return {c, -s};
+    }
+    const double d2 = d * d;
+    double s = fma(d2, -1.0 / 39916800.0, 1.0 / 362880.0);
+    s = fma(d2, s, -1.0 / 5040.0);
+    s = fma(d2, s, 1.0 / 120.0);
+    s = fma(d2, s, -1.0 / 6.0);
+    s = fma(d2 * d, s, d);
+    double c = fma(d2, 1.0 / 479001600.0, -1.0 / 3628800.0);
+    c = fma(d2, c, 1.0 / 40320.0);
+    c = fma(d2, c, -1.0 / 720.0);
+    c = fma(d2, c, 1.0 / 24.0);
+    c = fma(d2, c, -0.5);
+    c = fma(d2, c, 1.0);
+    return {c, -s};
+}
+
 struct LoSteps {
-    cplx z1, z2;
+    cplx z1, z2;        // exp(-j*inc1), exp(-j*inc2)
     double inc1, inc2;
 };
 
 OPVD_HD LoSteps lo_steps(double freq_offset) {
     LoSteps l;
-    l.inc1 = kTwoPi * (-kFreqDev + freq_offset) / kSampleRate;
-    l.inc2 = kTwoPi * (+kFreqDev + freq_offset) / kSampleRate;
-    double s, c;
-    sincos(l.inc1, &s, &c);
-    l.z1 = {c, -s};
-    sincos(l.inc2, &s, &c);
-    l.z2 = {c, -s};
+    double d;
+    const cplx zeta = zeta_from_offset(freq_offset, d);
+    l.inc1 = d - kIncDev;
+    l.inc2 = d + kIncDev;
+    l.z1 = cmul(cplx{kTauC, kTauS}, zeta);   // exp(+j*2pi/160) * exp(-j*delta)
+    l.z2 = cmul(cplx{kTauC, -kTauS}, zeta);
     return l;
 }
 
-OPVD_HD double wrap_phase(double ph) {  // :259-262
-    while (ph > kPi) ph -= kTwoPi;
-    while (ph < -kPi) ph += kTwoPi;
-    return ph;
+// one tone only (tone 0 -> F1, tone 1 -> F2): used when the two tones live on different lanes
+OPVD_HD void lo_step_tone(double freq_offset, int tone, cplx& z, double& inc) {
+    double d;
+    const cplx zeta = zeta_from_offset(freq_offset, d);
+    inc = tone ? d + kIncDev : d - kIncDev;
+    z = cmul(cplx{kTauC, tone ? -kTauS : kTauS}, zeta);
+}
+
+OPVD_HD double wrap_phase(double ph) {  // (-pi, pi] up to rounding; only the signed-zero corner reads it
+    return fma(-kTwoPi, rint(ph * kInvTwoPi), ph);
 }
 
 // Horner over 5 consecutive samples: s0 + z*(s1 + z*(s2 + z*(s3 + z*s4)))
@@ -111,6 +152,17 @@ struct Gates {
     cplx E, O, L;  // interpolated early / on-time / late sums (common unit-modulus phase factor dropped)
 };
 
+// s*z40 - f0  for real-pair samples: shifted-window correction dX = s[last+1]*z^40 - s[first]
+OPVD_HD cplx edge_term(double lastI, double lastQ, double firstI, double firstQ, cplx z40) {
+    return {fma(lastI, z40.r, fma(-lastQ, z40.i, -firstI)), fma(lastI, z40.i, fma(lastQ, z40.r, -firstQ))};
+}
+
+// interpolator applied after the sums: g*X + h*dX
+OPVD_HD void interp_weights(cplx z, double f, cplx& g, cplx& h) {
+    h = {f * z.r, -(f * z.i)};       // f*conj(z)
+    g = {(1.0 - f) + h.r, h.i};      // (1-f) + f*conj(z)
+}
+
 // combine six 10-sample partial sums H[m] (samples 10m-10 .. 10m-1 relative to b, exponent origin at
 // the segment start) into the three 40-sample gates and apply the interpolator.
 // sI/sQ: raw samples at local indices -10, 0, 10, 30, 40, 50  (window slots 0,10,20,40,50,60)
@@ -123,17 +175,39 @@ OPVD_HD Gates combine_gates(const cplx* H, const TonePowers& p, double f, const 
     cplx E = cfma(p.q2, T23, T01);
     cplx O = cfma(p.q2, T34, T12);
     cplx L = cfma(p.q2, T45, T23);
-    // shifted-window corrections dX = s[last+1]*z^40 - s[first]
-    cplx dE = {fma(sI[3], p.z40.r, fma(-sQ[3], p.z40.i, -sI[0])), fma(sI[3], p.z40.i, fma(sQ[3], p.z40.r, -sQ[0]))};
-    cplx dO = {fma(sI[4], p.z40.r, fma(-sQ[4], p.z40.i, -sI[1])), fma(sI[4], p.z40.i, fma(sQ[4], p.z40.r, -sQ[1]))};
-    cplx dL = {fma(sI[5], p.z40.r, fma(-sQ[5], p.z40.i, -sI[2])), fma(sI[5], p.z40.i, fma(sQ[5], p.z40.r, -sQ[2]))};
-    cplx h = {f * p.z.r, -(f * p.z.i)};   // f*conj(z)
-    cplx g = {(1.0 - f) + h.r, h.i};      // (1-f) + f*conj(z)
+    cplx dE = edge_term(sI[3], sQ[3], sI[0], sQ[0], p.z40);
+    cplx dO = edge_term(sI[4], sQ[4], sI[1], sQ[1], p.z40);
+    cplx dL = edge_term(sI[5], sQ[5], sI[2], sQ[2], p.z40);
+    cplx g, h;
+    interp_weights(p.z, f, g, h);
     Gates o;
     o.E = cfma(g, E, cmul(h, dE));
     o.O = cfma(g, O, cmul(h, dO));
     o.L = cfma(g, L, cmul(h, dL));
     return o;
+}
+
+// early-gate correction for the first symbol of a call: y[k] := samples[0] for local k = -10..-1 (:237).
+// Returns sum_{k=0..9} (y[k-10] - s0) z^k, to be subtracted from the generic early sum.
+OPVD_HD cplx first_symbol_fix(const uint32_t* win, double f, cplx z) {
+    double I0, Q0;
+    unpack_iq(win[kWinLead], I0, Q0);
+    cplx fix = {0.0, 0.0};
+    for (int k = 9; k >= 0; --k) {
+        double Ia, Qa, Ib, Qb;
+        unpack_iq(win[k], Ia, Qa);
+        unpack_iq(win[k + 1], Ib, Qb);
+        const double yr = fma(f, Ib - Ia, Ia) - I0;
+        const double yi = fma(f, Qb - Qa, Qa) - Q0;
+        fix = {fma(fix.r, z.r, fma(-fix.i, z.i, yr)), fma(fix.r, z.i, fma(fix.i, z.r, yi))};
+    }
+    return fix;
+}
+
+// timing error detector on the dominant tone's gates (:271-280)
+OPVD_HD double ted_from_gates(cplx early, cplx late) {
+    const double ee = cnorm(early), el = cnorm(late);
+    return (el - ee) / (el + ee + 1e-10);
 }
 
 // AFC phase detector when dom or prev is exactly zero: reproduce the reference's signed zeros.
@@ -153,16 +227,38 @@ OPVD_HD double afc_phase_signed_zero(cplx dom, cplx prev, double ph) {
     return atan2(xi, xr);
 }
 
-// Loop-carried registers of one stream while a kernel is running.
+// arg(dom * conj(prev)) (:299)
+OPVD_HD double afc_phase(cplx dom, cplx prev, double ph) {
+    const bool dz = (dom.r == 0.0 && dom.i == 0.0), pz = (prev.r == 0.0 && prev.i == 0.0);
+    if (dz || pz) return afc_phase_signed_zero(dom, prev, ph);
+    const double xr = fma(dom.r, prev.r, dom.i * prev.i);
+    const double xi = fma(dom.i, prev.r, -(dom.r * prev.i));
+    return atan2(xi, xr);
+}
+
+// 2nd-order timing loop (:283-286); returns timing_adj
+OPVD_HD double timing_loop(double& timing_freq, double ted) {
+    timing_freq += 0.00001 * ted;
+    timing_freq = clampd(timing_freq, -0.1, 0.1);
+    return clampd(0.005 * ted + timing_freq, -2.0, 2.0);
+}
+
+// AFC loop (:300-303)
+OPVD_HD void afc_loop(double& freq_offset, double pd, double afc_alpha) {
+    const double ferr = pd * kSymRateOverTwoPi;
+    freq_offset += afc_alpha * ferr;
+    freq_offset = clampd(freq_offset, -2000.0, 2000.0);
+}
+
+// Loop-carried registers of one stream while a kernel is running (both tones on one lane).
 struct DemodRegs {
     double freq_offset, ph1, ph2, pos, timing_freq;
     cplx p1, p2;
     LoSteps lo;
 };
 
-// One symbol.  win[0..60] = packed raw samples at local indices b-10 .. b+50 (b = floor(pos)).
-// first_in_call: the early gate must see samples[0] for local indices < 0 (:237) and the AFC update
-// is skipped (:289); `s0` is the packed sample at local index 0 in that case.
+// One symbol, both tones on this lane.  win[0..60] = packed raw samples at local indices b-10 .. b+50.
+// first_in_call: early-gate clamp (:237) and no AFC update (:289).
 OPVD_HD double demod_symbol(DemodRegs& r, const uint32_t* win, double f, bool first_in_call, double afc_alpha) {
     const TonePowers pw1 = tone_powers(r.lo.z1);
     const TonePowers pw2 = tone_powers(r.lo.z2);
@@ -190,19 +286,7 @@ OPVD_HD double demod_symbol(DemodRegs& r, const uint32_t* win, double f, bool fi
     Gates g2 = combine_gates(H2, pw2, f, sI, sQ);
 
     if (first_in_call) {
-        // early gate: y[k] := samples[0] for k = -10..-1  (:237).  Remove what the generic path summed
-        // for those ten taps and add the clamped value instead.
-        double I0 = sI[1], Q0 = sQ[1];
-        cplx fix1 = {0.0, 0.0}, fix2 = {0.0, 0.0};
-        for (int k = 9; k >= 0; --k) {  // Horner over exponents k = 0..9 (tap local index k-10)
-            double Ia, Qa, Ib, Qb;
-            unpack_iq(win[k], Ia, Qa);
-            unpack_iq(win[k + 1], Ib, Qb);
-            double yr = fma(f, Ib - Ia, Ia) - I0;  // y[k-10] - s0
-            double yi = fma(f, Qb - Qa, Qa) - Q0;
-            fix1 = {fma(fix1.r, pw1.z.r, fma(-fix1.i, pw1.z.i, yr)), fma(fix1.r, pw1.z.i, fma(fix1.i, pw1.z.r, yi))};
-            fix2 = {fma(fix2.r, pw2.z.r, fma(-fix2.i, pw2.z.i, yr)), fma(fix2.r, pw2.z.i, fma(fix2.i, pw2.z.r, yi))};
-        }
+        const cplx fix1 = first_symbol_fix(win, f, pw1.z), fix2 = first_symbol_fix(win, f, pw2.z);
         g1.E.r -= fix1.r; g1.E.i -= fix1.i;
         g2.E.r -= fix2.r; g2.E.i -= fix2.i;
     }
@@ -212,15 +296,8 @@ OPVD_HD double demod_symbol(DemodRegs& r, const uint32_t* win, double f, bool fi
     const double soft = e2 - e1;  // :268
     const bool tone1 = e1 > e2;   // :272, :291
 
-    // timing error detector + 2nd-order loop (:271-286)
-    const cplx ge = tone1 ? g1.E : g2.E;
-    const cplx gl = tone1 ? g1.L : g2.L;
-    const double ee = cnorm(ge), el = cnorm(gl);
-    const double ted = (el - ee) / (el + ee + 1e-10);
-    r.timing_freq += 0.00001 * ted;
-    r.timing_freq = clampd(r.timing_freq, -0.1, 0.1);
-    double timing_adj = 0.005 * ted + r.timing_freq;
-    timing_adj = clampd(timing_adj, -2.0, 2.0);
+    const double ted = ted_from_gates(tone1 ? g1.E : g2.E, tone1 ? g1.L : g2.L);
+    const double timing_adj = timing_loop(r.timing_freq, ted);
 
     // previous correlations for the NEXT symbol: rotate this symbol's on-time sums to the phase
     // frame at the next symbol start (phase advances by 40*inc of THIS symbol)
@@ -228,20 +305,8 @@ OPVD_HD double demod_symbol(DemodRegs& r, const uint32_t* win, double f, bool fi
     const cplx n2 = cmul(g2.O, cconj(pw2.z40));
 
     if (!first_in_call) {  // :289-307
-        const cplx dom = tone1 ? g1.O : g2.O;
-        const cplx prev = tone1 ? r.p1 : r.p2;
-        double pd;
-        const bool dz = (dom.r == 0.0 && dom.i == 0.0), pz = (prev.r == 0.0 && prev.i == 0.0);
-        if (dz || pz) {
-            pd = afc_phase_signed_zero(dom, prev, tone1 ? r.ph1 : r.ph2);
-        } else {
-            const double xr = fma(dom.r, prev.r, dom.i * prev.i);
-            const double xi = fma(dom.i, prev.r, -(dom.r * prev.i));
-            pd = atan2(xi, xr);
-        }
-        const double ferr = pd * kSymbolRate / kTwoPi;
-        r.freq_offset += afc_alpha * ferr;
-        r.freq_offset = clampd(r.freq_offset, -2000.0, 2000.0);
+        const double pd = afc_phase(tone1 ? g1.O : g2.O, tone1 ? r.p1 : r.p2, tone1 ? r.ph1 : r.ph2);
+        afc_loop(r.freq_offset, pd, afc_alpha);
     }
     // absolute phases advance with the increments used during this symbol (:250-262)
     r.ph1 = wrap_phase(fma(40.0, r.lo.inc1, r.ph1));
@@ -279,7 +344,7 @@ OPVD_HD bool demod_schedule(DemodState& s, double& pos, int mode, int64_t avail,
             const int64_t remaining = avail - s.origin;
             if (mode == kModeBatch) {
                 if (!final) return false;  // batch = load everything, then process
-                s.call_len = avail;        // may be 0: the loop condition below closes it at once
+                s.call_len = avail;
                 if (avail == 0) { s.flags |= kFlagDone; return false; }
             } else if (remaining >= kChunkSamples) {
                 s.call_len = kChunkSamples;

@@ -150,7 +150,7 @@ __device__ __forceinline__ float2 clean_sample(const uint8_t* __restrict__ syms,
 
 __global__ void synth_wave_kernel(SynthParams p, uint32_t* __restrict__ iq, const uint8_t* __restrict__ syms,
                                   const int8_t* __restrict__ fsign) {
-    const int stream = blockIdx.y;
+    for (int stream = blockIdx.y; stream < p.n_streams; stream += gridDim.y) {
     const StreamImpair im = stream_impair(p, p.first_stream + stream);
     const long long n_sig = (long long)p.n_frames * kFrameSymbols * kSps;
     const uint8_t* ssyms = syms + (long long)stream * p.n_frames * kFrameSymbols;
@@ -191,6 +191,7 @@ __global__ void synth_wave_kernel(SynthParams p, uint32_t* __restrict__ iq, cons
         const int iQ = max(-32768, min(32767, __float2int_rn(Q)));
         row[n] = (uint32_t)(iI & 0xFFFF) | ((uint32_t)(iQ & 0xFFFF) << 16);
     }
+    }  // stream
 }
 
 size_t synth_scratch_bytes(const SynthParams& p) {
@@ -207,7 +208,7 @@ void launch_synth(const SynthParams& p, uint32_t* iq, uint8_t* scratch_syms, int
     long long bx = (p.n_samples + 255) / 256;
     if (bx > 4096) bx = 4096;
     if (bx < 1) bx = 1;
-    dim3 grid((unsigned)bx, (unsigned)p.n_streams);
+    dim3 grid((unsigned)bx, (unsigned)(p.n_streams < 65535 ? p.n_streams : 65535));
     synth_wave_kernel<<<grid, 256, 0, st>>>(p, iq, scratch_syms, scratch_sign);
 }
 

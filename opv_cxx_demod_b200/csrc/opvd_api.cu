@@ -278,6 +278,34 @@ int opvd_destroy(opvd_handle* h) {
     return OPVD_OK;
 }
 
+int opvd_reset(opvd_handle* h) {
+    if (!h) return OPVD_ERR_ARG;
+    CK(cudaSetDevice(h->dev));
+    CK(cudaStreamSynchronize(h->st));
+    const int have_init = (h->cfg.mode == OPVD_MODE_STREAM && h->cfg.have_init_offset) ? 1 : 0;
+    init_state_kernel<<<(h->S + 127) / 128, 128, 0, h->st>>>(h->d_dstate, h->d_tstate, h->d_est, h->S, have_init,
+                                                            h->cfg.init_offset_hz);
+    CK(cudaMemsetAsync(h->d_nevents, 0, sizeof(int32_t) * h->S, h->st));
+    CK(cudaMemsetAsync(h->d_ntasks, 0, sizeof(int32_t), h->st));
+    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * kNumCounters, h->st));
+    if (h->d_metrics)
+        CK(cudaMemsetAsync(h->d_metrics, 0xFF, (size_t)h->S * h->max_frames * sizeof(int32_t), h->st));
+    std::fill(h->polled_frames.begin(), h->polled_frames.end(), 0);
+    std::fill(h->polled_events.begin(), h->polled_events.end(), 0);
+    if (!h->attached) {  // library-owned input starts empty again; attached captures stay attached
+        std::fill(h->h_avail.begin(), h->h_avail.end(), 0);
+        h->avail_dirty = true;
+    }
+    h->row_base = 0;
+    h->soft_base = 0;
+    h->mirror_stale = h->ev_mirror_stale = true;
+    h->final_seen = false;
+    h->have_times = false;
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaGetLastError());
+    return OPVD_OK;
+}
+
 static int push_common(opvd_handle* h, int32_t first, int32_t count, const int16_t* iq, int64_t n, int64_t host_stride) {
     if (!h || n < 0 || (n > 0 && !iq)) return OPVD_ERR_ARG;
     if (h->attached || !h->d_iq_owned) return OPVD_ERR_STATE;

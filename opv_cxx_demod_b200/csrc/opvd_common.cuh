@@ -57,20 +57,18 @@ OPVD_HD double cnorm(cplx a) { return fma(a.r, a.r, a.i * a.i); }
 
 OPVD_HD double clampd(double v, double lo, double hi) { return (v < lo) ? lo : ((hi < v) ? hi : v); }
 
-// exact int16 -> double.  On the device this is one LOP + one DADD (FP64 pipe) instead of the
-// quarter-rate I2F.F64 conversion: build 2^52 + 2^31 + v in the mantissa and subtract the bias.
-OPVD_HD double i16_to_f64(int v) {
-#if defined(__CUDA_ARCH__)
-    return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;
-#else
-    return (double)v;
-#endif
-}
-
-// packed sample word (I in bits 0..15, Q in bits 16..31, both signed) -> doubles
+// packed sample word (I in bits 0..15, Q in bits 16..31, both signed) -> doubles (exact).
+// On sm_100a each half converts with ONE instruction straight from the packed register
+// (I2F.F64.S16 R, Rw / I2F.F64.S16 R, Rw.H1); OPVD_CVT_MAGIC selects the alternative
+// 2^52-bias trick (LOP3 + DADD on the FP64 pipe) for comparison.
 OPVD_HD void unpack_iq(uint32_t w, double& I, double& Q) {
-    I = i16_to_f64((int)(int16_t)(w & 0xFFFFu));
-    Q = i16_to_f64((int)(int32_t)w >> 16);
+#if defined(__CUDA_ARCH__) && defined(OPVD_CVT_MAGIC)
+    I = __hiloint2double(0x43300000, (int)((w & 0xFFFFu) ^ 0x8000u)) - 4503599627403264.0;  // 2^52 + 2^15
+    Q = __hiloint2double(0x43300000, (int)((w >> 16) ^ 0x8000u)) - 4503599627403264.0;
+#else
+    I = (double)(int16_t)(w & 0xFFFFu);
+    Q = (double)(int16_t)(w >> 16);
+#endif
 }
 
 }  // namespace opvd

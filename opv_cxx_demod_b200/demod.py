@@ -113,6 +113,10 @@ class DemodBank:
         if sync:
             self.sync()
 
+    def reset(self) -> None:
+        """Fresh demodulator / tracker / decoder state for every stream; buffers and attached captures are kept."""
+        self._ck(self._lib.opvd_reset(self._h), "opvd_reset")
+
     def sync(self) -> None:
         self._ck(self._lib.opvd_sync(self._h), "opvd_sync")
 

@@ -55,11 +55,13 @@ def _run_bank(pkg, caps, streaming, **kw):
     return bank
 
 
+@pytest.mark.parametrize("lanes", [1, 2, 4])
 @pytest.mark.parametrize("streaming", [False, True])
-def test_all_cases_one_bank_vs_oracle_and_golden(streaming, pkg, cases, ora):
-    """All standard captures as ONE ragged multi-stream bank: frames / events / soft / offsets per stream."""
+def test_all_cases_one_bank_vs_oracle_and_golden(streaming, lanes, pkg, cases, ora):
+    """All standard captures as ONE ragged multi-stream bank: frames / events / soft / offsets per stream,
+    for every lanes-per-stream variant of the demodulator kernel."""
     caps = [cases[n] for n in NAMES]
-    bank = _run_bank(pkg, caps, streaming)
+    bank = _run_bank(pkg, caps, streaming, lanes_per_stream=lanes)
     fr = bank.poll_frames()
     problems = []
     for s, name in enumerate(NAMES):

@@ -50,6 +50,16 @@ __global__ void k(unsigned long long* out, int iters, double seed) {
             for (int i = 0; i < 4; ++i) a[i] = __shfl_sync(0xffffffffu, a[i], (tid + it) & 31);
         unsigned s = 0; for (int i = 0; i < 4; ++i) s += a[i];
         if (s == 12345u) out[0] = 1;
+    } else if (OP == 6) {  // I2F.F64.S16 (sample unpack) interleaved with a DADD so it cannot be hoisted
+        double a[8];
+        unsigned w = (unsigned)seed * 2654435761u + tid;
+        for (int i = 0; i < 8; ++i) a[i] = 0.0;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a[i] += (double)(short)((w >> ((i & 1) * 16)) & 0xFFFFu); w = w * 1664525u + 1013904223u; }
+        }
+        double s = 0; for (int i = 0; i < 8; ++i) s += a[i];
+        if (s == 12345.678) out[0] = 1;
     } else if (OP == 5) {  // dependent DFMA chain: latency
         double a = seed + tid;
         for (int it = 0; it < iters * 8; ++it) a = fma(a, 1.0000001, 1e-9);
@@ -76,14 +86,14 @@ int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     const int sms = p.multiProcessorCount, grid = sms * 8, block = 256, iters = 20000;
     double dfma = run<0>(grid, block, iters, 8), ffma = run<1>(grid, block, iters, 8), alu = run<2>(grid, block, iters, 16),
-           dpx = run<3>(grid, block, iters, 8), shfl = run<4>(grid, block, iters, 4);
+           dpx = run<3>(grid, block, iters, 8), shfl = run<4>(grid, block, iters, 4), i2f = run<6>(grid, block, iters, 8);
     // latency: one warp per SM
     double chain = run<5>(sms, 32, 4000, 8);  // dependent ops/s over sms*32 threads
     int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz_max\": %d, \"dfma_per_s\": %.4g, \"fp64_tflops\": %.3f, "
            "\"ffma_per_s\": %.4g, \"fp32_tflops\": %.3f, \"alu_ops_per_s\": %.4g, \"dpx_vibmin_add_per_s\": %.4g, "
-           "\"shfl_per_s\": %.4g, \"dfma_dependent_ns\": %.3f}\n",
-           p.name, sms, clk, dfma, 2 * dfma / 1e12, ffma, 2 * ffma / 1e12, alu, dpx, shfl,
+           "\"shfl_per_s\": %.4g, \"i2f_f64_s16_plus_dadd_per_s\": %.4g, \"dfma_dependent_ns\": %.3f}\n",
+           p.name, sms, clk, dfma, 2 * dfma / 1e12, ffma, 2 * ffma / 1e12, alu, dpx, shfl, i2f,
            1e9 / (chain / (sms * 32.0)));
     return 0;
 }
