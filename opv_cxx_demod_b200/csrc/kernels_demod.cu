@@ -309,6 +309,8 @@ int demod_auto_lanes(int n_streams) {
     // redundant loop arithmetic, so take the smallest split that fills the machine
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // small banks are bound by the per-symbol latency of the serial recurrence: one warp per stream
+    if ((long long)n_streams <= 28ll * sms) return 32;
     const long long want_warps = 12ll * sms;
     if ((long long)n_streams / 32 >= want_warps) return 1;
     if ((long long)n_streams / 16 >= want_warps) return 2;
@@ -320,6 +322,7 @@ cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodSt
                          unsigned long long* counters, cudaStream_t st) {
     if (n_streams <= 0) return cudaSuccess;
     int L = lanes_per_stream > 0 ? lanes_per_stream : demod_auto_lanes(n_streams);
+    if (L >= 32) return launch_demod_warp(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     if (L >= 4) return launch_t<1, 2>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     if (L >= 2) return launch_t<1, 1>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     return launch_t<2, 1>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);

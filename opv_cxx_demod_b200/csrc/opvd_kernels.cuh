@@ -50,10 +50,15 @@ struct SoftBuffers {
 void launch_estimate(const StreamBuffers& sb, DemodState* dstate, double* est_out, int n_streams, int mode,
                      int final_flag, cudaStream_t st);
 
-// lanes_per_stream in {1}; returns cudaError
+// lanes_per_stream in {1, 2, 4, 32}; 0 = chosen from the stream count; returns cudaError
 cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                          int mode, int final_flag, double afc_alpha, int lanes_per_stream,
                          unsigned long long* counters, cudaStream_t st);
+
+// warp-per-stream variant (kernels_demod_warp.cu); selected by launch_demod for lanes_per_stream == 32
+cudaError_t launch_demod_warp(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
+                              int mode, int final_flag, double afc_alpha, unsigned long long* counters,
+                              cudaStream_t st);
 
 void launch_track(const SoftBuffers& so, const DemodState* dstate, TrackState* tstate, int n_streams,
                   FrameRec* frec, int max_frames, TrackEvent* events, int32_t* n_events, int max_events,

@@ -8,6 +8,7 @@
 #include <vector>
 #include <cmath>
 #include "../../opv_cxx_demod_b200/csrc/demod_core.cuh"
+#include "../../opv_cxx_demod_b200/csrc/demod_warp_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/est_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/track_core.cuh"
 
@@ -69,6 +70,83 @@ size_t hostsim_demod(const int16_t* iq, size_t n, int mode, double afc_alpha, in
     if (est_out) *est_out = est;
     if (final_freq) *final_freq = st.freq_offset;
     if (final_tfreq) *final_tfreq = st.timing_freq;
+    return ns;
+}
+
+// whole stream through the WARP-PER-STREAM lane decomposition (demod_warp_core.cuh): the 32 lanes are
+// simulated in lock step, warp shuffles become array indexing.  Same contract as hostsim_demod.
+size_t hostsim_demod_warp(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
+                          double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
+    std::vector<uint32_t> w(n + 64 + 64, 0xDEADBEEFu);
+    for (size_t i = 0; i < n; ++i)
+        w[64 + i] = (uint32_t)(uint16_t)iq[2 * i] | ((uint32_t)(uint16_t)iq[2 * i + 1] << 16);
+    const uint32_t* base = w.data() + 64;
+
+    DemodState st;
+    demod_state_init(st);
+    double est = 0.0;
+    if (mode == kModeBatch) {
+        est = hostsim_estimate(iq, n);
+        st.freq_offset = est;
+    } else if (have_init) {
+        st.freq_offset = init_offset;
+    } else if (n >= (size_t)kChunkSamples) {
+        est = hostsim_estimate(iq, kChunkSamples);
+        st.freq_offset = est;
+    }
+    st.flags |= kFlagEstDone;
+
+    WarpLane wl[32];
+    for (int l = 0; l < 32; ++l) {
+        warp_lane_init(wl[l], l);
+        warp_lane_lo(wl[l], st.freq_offset);
+        wl[l].prev = wl[l].tone ? st.p2 : st.p1;
+    }
+    double freq_offset = st.freq_offset, pos = st.pos, timing_freq = st.timing_freq, ph1 = st.ph1, ph2 = st.ph2;
+    auto down = [](const cplx* v, int l, int d) { return (l + d < 32) ? v[l + d] : v[l]; };
+    size_t ns = 0;
+    while (demod_schedule(st, pos, mode, (int64_t)n, true)) {
+        const int64_t b = (int64_t)pos;
+        const double f = pos - (double)b;
+        const uint32_t* win = base + st.origin + b - kWinLead;
+        const bool first = st.sym_in_call == 0;
+        cplx W[32], F[32], A[32], B[32], Cc[32], X[32], Ou[32];
+        double nrm[32], pdo[32];
+        for (int l = 0; l < 32; ++l) {
+            const int pc = wl[l].p > 12 ? 12 : wl[l].p;
+            uint32_t s5[5];
+            for (int r = 0; r < 5; ++r) s5[r] = (5 * pc + r <= 60) ? win[5 * pc + r] : 0x12345678u;  // beyond the window: junk, unused
+            LanePartial lp = warp_lane_partial(wl[l], s5);
+            W[l] = lp.W; F[l] = lp.F;
+        }
+        for (int l = 0; l < 32; ++l) { cplx o = down(W, l, 1); A[l] = {W[l].r + o.r, W[l].i + o.i}; }
+        for (int l = 0; l < 32; ++l) { cplx o = down(A, l, 2); B[l] = {A[l].r + o.r, A[l].i + o.i}; }
+        for (int l = 0; l < 32; ++l) { cplx o = down(B, l, 4); Cc[l] = {B[l].r + o.r, B[l].i + o.i}; }
+        for (int l = 0; l < 32; ++l) X[l] = warp_lane_gate(wl[l], f, Cc[l], down(F, l, 8), F[l]);
+        if (first) {
+            auto acc = [&](int k) { return win[k]; };
+            for (int l = 0; l < 32; l += 16) {
+                const cplx fix = first_symbol_fix_w(acc, f, wl[l].z);
+                X[l].r -= fix.r; X[l].i -= fix.i;
+            }
+        }
+        for (int l = 0; l < 32; ++l) nrm[l] = cnorm(X[l]);
+        bool tone1;
+        const double soft = warp_uniform_timing(nrm[2], nrm[18], nrm[0], nrm[4], nrm[16], nrm[20], timing_freq, pos, tone1);
+        for (int l = 0; l < 32; ++l) pdo[l] = warp_lane_afc_phase(wl[l], X[l], wl[l].tone ? ph2 : ph1, first, Ou[l]);
+        if (!first) afc_loop(freq_offset, pdo[tone1 ? 2 : 18], afc_alpha);
+        for (int l = 0; l < 32; ++l) wl[l].prev = cmul(Ou[l], cconj(wl[(l & 16) | kWarpLaneZ40].R));
+        ph1 = wrap_phase(fma(40.0, wl[0].inc, ph1));
+        ph2 = wrap_phase(fma(40.0, wl[16].inc, ph2));
+        if (!first) for (int l = 0; l < 32; ++l) warp_lane_lo(wl[l], freq_offset);
+        st.sym_in_call++;
+        if (ns < cap) soft_out[ns] = soft;
+        ++ns;
+        st.n_sym++;
+    }
+    if (est_out) *est_out = est;
+    if (final_freq) *final_freq = freq_offset;
+    if (final_tfreq) *final_tfreq = timing_freq;
     return ns;
 }
 
