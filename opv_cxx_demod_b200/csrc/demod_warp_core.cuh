@@ -24,6 +24,7 @@
 // from an Estrin-form Taylor polynomial), so z and R_c are ready together.
 #pragma once
 #include "demod_core.cuh"
+#include "fastmath.cuh"
 
 namespace opvd {
 
@@ -70,13 +71,13 @@ struct WarpLane {
     cplx prev;       // previous on-time correlation in the next symbol's phase frame (gate lane O only)
 };
 
-OPVD_HD void warp_lane_init(WarpLane& w, int lane) {
+OPVD_HD void warp_lane_init(WarpLane& w, int lane, const FastMathTable& K) {
     w.tone = lane >> 4;
     w.p = lane & 15;
     const int pc = w.p > 12 ? 12 : w.p;
     w.c = 5.0 * pc;
     w.sgn = w.tone ? 1.0 : -1.0;
-    w.tau1 = {kTauC, w.tone ? -kTauS : kTauS};
+    w.tau1 = {K.tau_c, w.tone ? -K.tau_s : K.tau_s};
     // exp(-j*sgn*2*pi*c/160) with exact argument reduction: angle = pi * (5 pc) / 80
     double s, c;
 #if defined(__CUDA_ARCH__)
@@ -115,22 +116,42 @@ OPVD_HD LanePartial warp_lane_partial(const WarpLane& w, const uint32_t* s) {
     return o;
 }
 
-// Interpolated gate on a gate-owner lane: C = sum of the 8 lane partials starting here,
-// Fh = F of lane p+8, F = own F.
-OPVD_HD cplx warp_lane_gate(const WarpLane& w, double f, cplx C, cplx Fh, cplx F) {
-    cplx g, h;
-    interp_weights(w.z, f, g, h);
-    const cplx dX = {Fh.r - F.r, Fh.i - F.i};
-    return cfma(g, C, cmul(h, dX));
+// LO step and slot rotation in the hot loop: valid for |freq_offset| <= 2.2 kHz, which the AFC clamp
+// (:303) guarantees after every update.  Short Taylor polynomial for z, Estrin form for R_c.
+OPVD_HD void warp_lane_lo_fast(WarpLane& w, double freq_offset, const FastMathTable& K) {
+    const double d = freq_offset * K.two_pi_over_fs;
+    w.inc = fma(w.sgn, K.inc_dev, d);
+    w.z = cmul(w.tau1, expmj_small(d, K));
+    w.R = cmul(w.tauc, expmj_mid(w.c * d, K));
 }
 
-// AFC phase detector on gate lane O (:289-299).  X = interpolated O' (still carrying z^10 = R of
-// this lane); returns arg(O_n * conj(prev)) and the un-rotated on-time correlation in Ou.
-OPVD_HD double warp_lane_afc_phase(const WarpLane& w, cplx X, double ph, bool first, cplx& Ou) {
-    Ou = cmul(X, cconj(w.R));
-    if (first) return 0.0;
-    return afc_phase(Ou, w.prev, ph);
+// Interpolated gate on a gate-owner lane: C = sum of the 8 lane partials starting here,
+// Fh = F of lane p+8, F = own F.  With dX = Fh - F (shifted-window edge term):
+//   X = (1-f)*C + f*conj(z)*(C + dX) = C + f*(conj(z)*(C + dX) - C)
+OPVD_HD cplx warp_lane_gate(const WarpLane& w, double f, cplx C, cplx Fh, cplx F) {
+    const cplx S = {C.r + (Fh.r - F.r), C.i + (Fh.i - F.i)};
+    const cplx T = {fma(w.z.r, S.r, w.z.i * S.i), fma(w.z.r, S.i, -(w.z.i * S.r))};  // conj(z) * S
+    return {fma(f, T.r - C.r, C.r), fma(f, T.i - C.i, C.i)};
 }
+
+// AFC phase detector on gate lane O (:289-299).  X = interpolated O' (carrying z^10 = R of this lane),
+// RP = R * prev, so X * conj(RP) = O_n * conj(prev).  corner: O_n or prev exactly zero (all-zero
+// input) -> reproduce the reference's signed zeros through the slow path.
+OPVD_HD_COLD double afc_phase_corner(cplx dom, cplx prev, double ph) { return afc_phase_signed_zero(dom, prev, ph); }
+
+OPVD_HD double warp_lane_afc_phase(const WarpLane& w, cplx X, cplx RP, bool corner, double ph,
+                                   const FastMathTable& K) {
+    const double xr = fma(X.r, RP.r, X.i * RP.i);
+    const double xi = fma(X.i, RP.r, -(X.r * RP.i));
+    double pd = atan2_fast(xi, xr, K);  // branch-free; NaN in the corner case, replaced below
+    // the rare fix-up comes AFTER the fast evaluation so that the common path stays one basic block
+    // (the scheduler interleaves this chain with the timing loop's division)
+    if (corner) pd = afc_phase_corner(cmul(X, cconj(w.R)), w.prev, ph);
+    return pd;
+}
+
+// clamp to [-lim, lim] (same result as the reference's two comparisons for every non-NaN v)
+OPVD_HD double clamp_sym(double v, double lim) { return fabs(v) > lim ? copysign(lim, v) : v; }
 
 // early-gate correction for the first symbol of a call (:237), window read through an accessor
 // (win(k) = packed raw sample of slot k); same value as first_symbol_fix() in demod_core.cuh.
@@ -150,15 +171,23 @@ OPVD_HD cplx first_symbol_fix_w(Win win, double f, cplx z) {
     return fix;
 }
 
+// AFC loop (:300-303) and LO phase wrap (:259-262) with table constants
+OPVD_HD void warp_afc_loop(double& freq_offset, double pd, double afc_alpha, const FastMathTable& K) {
+    const double ferr = pd * K.sym_rate_over_two_pi;
+    freq_offset = clamp_sym(freq_offset + afc_alpha * ferr, 2000.0);
+}
+OPVD_HD double warp_wrap_phase(double ph, const FastMathTable& K) { return fma(-K.two_pi, rint(ph * K.inv_two_pi), ph); }
+
 // Uniform (all lanes redundantly) soft decision, TED and timing loop (:264-286, :313).
 // e1/e2 = |O|^2 per tone, eE*/eL* = early/late energies per tone.
 OPVD_HD double warp_uniform_timing(double e1, double e2, double eE1, double eL1, double eE2, double eL2,
-                                   double& timing_freq, double& pos, bool& tone1) {
+                                   double& timing_freq, double& pos, bool& tone1, const FastMathTable& K) {
     tone1 = e1 > e2;  // :272, :291
     const double ee = tone1 ? eE1 : eE2, el = tone1 ? eL1 : eL2;
-    const double ted = (el - ee) / (el + ee + 1e-10);
-    const double adj = timing_loop(timing_freq, ted);
-    pos += 40.0 + adj;
+    const double ted = div_fast(el - ee, el + ee + K.eps_ted);           // :280
+    timing_freq = clamp_sym(timing_freq + K.k_tf * ted, K.lim_tf);       // :283-284
+    const double adj = clamp_sym(K.k_adj * ted + timing_freq, 2.0);      // :285-286
+    pos += 40.0 + adj;                                          // :313
     return e2 - e1;  // :268
 }
 

@@ -50,10 +50,10 @@ constexpr int kSlotShift = 6;
 constexpr int kSlotSamples = 1 << kSlotShift;  // 64 samples = 256 B per bulk copy
 constexpr int kSlotBytes = kSlotSamples * 4;
 constexpr int kNumSlots = 8;
-constexpr int kRingWords = kNumSlots * kSlotSamples;  // 512 words = 2 KB per stream
-constexpr int kRingMask = kRingWords - 1;
+constexpr int kRingSamples = kNumSlots * kSlotSamples;     // 512 samples = 2 KB per stream
+constexpr int kRingWords = kRingSamples + kSlotSamples;    // + mirror of ring slot 0: windows never wrap
+constexpr int kRingMask = kRingSamples - 1;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kWarpsPerCta = 1;  // one stream per CTA spreads small banks evenly over the SMs
 
 __device__ __forceinline__ cplx shfl_down_c(cplx v, int d) {
     return {__shfl_down_sync(kFull, v.r, d), __shfl_down_sync(kFull, v.i, d)};
@@ -62,121 +62,80 @@ __device__ __forceinline__ cplx shfl_c(cplx v, int src) {
     return {__shfl_sync(kFull, v.r, src), __shfl_sync(kFull, v.i, src)};
 }
 
-}  // namespace
-
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
-demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
-                  int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
-    __shared__ __align__(128) uint32_t ring_all[kWarpsPerCta][kRingWords];
-    __shared__ __align__(8) unsigned long long mbar_all[kWarpsPerCta][kNumSlots];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int stream = blockIdx.x * kWarpsPerCta + wid;
-    if (stream >= n_streams) return;  // warp-uniform
-
-    const uint32_t* ring = ring_all[wid];
-    const uint32_t ring_s = smem_u32(ring_all[wid]);
-    const uint32_t mbar_s = smem_u32(mbar_all[wid]);
-    if (lane == 0) {
-#pragma unroll
-        for (int p = 0; p < kNumSlots; ++p) mbar_init(mbar_s + 8 * p, 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-
-    DemodState st = dstate[stream];
-    const long long avail = sb.avail[stream];
-    const long long row0 = sb.row_base;
-    const uint32_t* row = sb.iq + (long long)stream * sb.stride;  // row[r] holds absolute sample row0 + r
-    const int stride_i = (int)sb.stride;
-    const int avail_rel = (int)(avail - row0);
-    double* soft_row = so.soft + (long long)stream * so.stride - so.base;
-
+// Everything one warp carries through the symbol loop of its stream.
+struct WarpCtx {
+    FastMathTable K;     // polynomial / loop constants pinned in registers
     WarpLane wl;
-    warp_lane_init(wl, lane);
-    warp_lane_lo(wl, st.freq_offset);
-    wl.prev = wl.tone ? st.p2 : st.p1;
-    const int pc = wl.p > 12 ? 12 : wl.p;
-    const int lane_slot = 5 * pc;
-    const int tone_base = lane & 16;
+    cplx RP;             // R * prev (gate lane O): O_n * conj(prev) = X * conj(RP)
+    bool prev_zero;      // prev is exactly zero (signed-zero corner of the AFC phase detector)
+    double freq_offset, pos, timing_freq, ph_own, afc_alpha;
+    const uint32_t* ring;
+    uint32_t ring_s, mbar_s;
+    const uint32_t* row;
+    int stride_i, avail_rel, origin_rel;
+    int first_s, issued_s, ready_s;  // ring bookkeeping in samples relative to the row (multiples of 64)
+    int lane, lane_slot, tone_base;
+    double* soft_ptr;    // where the next soft symbol goes (lane 0 stores)
 
-    double freq_offset = st.freq_offset, pos = st.pos, timing_freq = st.timing_freq;
-    double ph_own = wl.tone ? st.ph2 : st.ph1;  // this lane's tone's absolute LO phase
+    __device__ __forceinline__ void issue_slot() {  // TMA bulk copy of the next 64-sample slot (lane 0)
+        if (lane == 0) {
+            const int p = (issued_s >> kSlotShift) & (kNumSlots - 1);
+            const int left = stride_i - issued_s;
+            const uint32_t bytes = left >= kSlotSamples ? (uint32_t)kSlotBytes : (uint32_t)(left * 4);
+            const uint32_t mb = mbar_s + 8 * p;
+            mbar_expect_tx(mb, p == 0 ? 2 * bytes : bytes);
+            tma_bulk_g2s(ring_s + p * kSlotBytes, row + issued_s, bytes, mb);
+            if (p == 0) tma_bulk_g2s(ring_s + kNumSlots * kSlotBytes, row + issued_s, bytes, mb);
+        }
+        issued_s += kSlotSamples;
+    }
+    __device__ __forceinline__ void wait_slot() {
+        const uint32_t mb = mbar_s + 8 * ((ready_s >> kSlotShift) & (kNumSlots - 1));
+        const uint32_t parity = (uint32_t)(((ready_s - first_s) >> (kSlotShift + 3)) & 1);
+        while (!mbar_try_wait(mb, parity)) {}
+        ready_s += kSlotSamples;
+    }
 
-    const long long n_sym0 = st.n_sym, origin0 = st.origin;
-    double call_len_d = (double)st.call_len;  // 0 => the slow path opens the next call
-    int origin_rel = (int)(st.origin - row0);
-    int a_first = -1, issued = 0, ready = 0;  // slot indices relative to the row (64-sample units)
-    long long n_sym = st.n_sym;
-    int sym_in_call = st.sym_in_call;
-
-    for (;;) {
-        if (!((pos + 40.0) + 10.0 < call_len_d)) {  // :221 fails or no call open: slow path (warp-uniform)
-            st.n_sym = n_sym;
-            st.sym_in_call = sym_in_call;
-            const bool live = demod_schedule(st, pos, mode, avail, final_flag != 0);
-            sym_in_call = st.sym_in_call;
-            call_len_d = (double)st.call_len;
-            origin_rel = (int)(st.origin - row0);
-            if (!live) break;
+    // keep 7 slots in flight ahead of the window starting at row index w0 (slot s recycles the ring
+    // position of slot s-8), and have everything up to w0 + kLookahead landed: that covers this
+    // symbol's window AND the next one's (it starts at most 42 samples later), so the next window can
+    // be loaded mid-symbol without another check.
+    static constexpr int kLookahead = (kWin - 1) + 44;
+    __device__ __forceinline__ void ring_maintain(int w0) {
+        while (w0 + (kNumSlots - 1) * kSlotSamples >= issued_s && issued_s < avail_rel) {
+            __syncwarp();  // every lane is done with the slot about to be recycled
+            issue_slot();
         }
-        const int b = __double2int_rz(pos);  // pos >= 0: truncation == floor (:125)
-        const double f = pos - (double)b;
-        const int w0 = origin_rel + b - kWinLead;  // row index of window slot 0 (>= -10)
-        const int a_lo = w0 >> kSlotShift, a_hi = (w0 + (kWin - 1)) >> kSlotShift;
-        __syncwarp();  // every lane is done with the ring slots about to be recycled
-        if (a_first < 0) {  // first symbol of this launch: prime the ring
-            a_first = a_lo < 0 ? 0 : a_lo;
-            issued = ready = a_first;
-        }
-        // prefetch: slot s overwrites the ring position of slot s-8, which must be behind the window
-        while (issued <= a_lo + (kNumSlots - 1) && (issued << kSlotShift) < avail_rel) {
-            if (lane == 0) {
-                const int p = issued & (kNumSlots - 1);
-                const int r0 = issued << kSlotShift;
-                const int left = stride_i - r0;
-                const uint32_t bytes = left >= kSlotSamples ? (uint32_t)kSlotBytes : (uint32_t)(left * 4);
-                const uint32_t mb = mbar_s + 8 * p;
-                mbar_expect_tx(mb, bytes);
-                tma_bulk_g2s(ring_s + p * kSlotBytes, row + r0, bytes, mb);
-            }
-            ++issued;
-        }
-        while (ready <= a_hi) {
-            if (ready >= a_first) {
-                const uint32_t mb = mbar_s + 8 * (ready & (kNumSlots - 1));
-                const uint32_t parity = (uint32_t)(((ready - a_first) >> 3) & 1);
-                while (!mbar_try_wait(mb, parity)) {}
-            }
-            ++ready;
-        }
-
-        // ---- lane partial sums over this lane's five slots
-        uint32_t s5[5];
-        const int w_lane = w0 + lane_slot;
+        while (w0 + kLookahead >= ready_s && ready_s < issued_s) wait_slot();
+    }
+    __device__ __forceinline__ void load_window(int b, uint32_t (&s5)[5]) const {
+        const uint32_t* src = ring + (((origin_rel + b - kWinLead) & kRingMask) + lane_slot);
 #pragma unroll
-        for (int r = 0; r < 5; ++r) s5[r] = ring[(w_lane + r) & kRingMask];
+        for (int r = 0; r < 5; ++r) s5[r] = src[r];
+    }
+
+    // One symbol at integer position b = trunc(pos), whose five lane samples are already in s5.
+    // Updates pos, then loads the NEXT symbol's samples into s5 and returns its b, before running the
+    // AFC chain, so that the loads and the AFC arithmetic overlap.  FIRST: first symbol of a
+    // demodulate() call (early-gate clamp :237, no AFC update :289).
+    template <bool FIRST>
+    __device__ __forceinline__ int symbol(int b, uint32_t (&s5)[5]) {
+        const double f = pos - (double)b;
+        // ---- lane partial sums over this lane's five slots
         const LanePartial lp = warp_lane_partial(wl, s5);
 
         // ---- gate sums: 8 consecutive lanes via shuffle-down 1, 2, 4; edge term from lane p+8
         const cplx Fh = shfl_down_c(lp.F, 8);
         cplx acc = lp.W;
-        {
-            const cplx o = shfl_down_c(acc, 1);
-            acc = {acc.r + o.r, acc.i + o.i};
-        }
-        {
-            const cplx o = shfl_down_c(acc, 2);
-            acc = {acc.r + o.r, acc.i + o.i};
-        }
-        {
-            const cplx o = shfl_down_c(acc, 4);
+#pragma unroll
+        for (int d = 1; d <= 4; d <<= 1) {
+            const cplx o = shfl_down_c(acc, d);
             acc = {acc.r + o.r, acc.i + o.i};
         }
         cplx X = warp_lane_gate(wl, f, acc, Fh, lp.F);
-        const bool first = sym_in_call == 0;
-        if (first) {  // early-gate clamp at the start of a call (:237); rare, warp-uniform branch
-            const cplx fix = first_symbol_fix_w([&](int k) { return ring[(w0 + k) & kRingMask]; }, f, wl.z);
+        if (FIRST) {
+            const uint32_t* win = ring + ((origin_rel + b - kWinLead) & kRingMask);
+            const cplx fix = first_symbol_fix_w([&](int k) { return win[k]; }, f, wl.z);
             if (wl.p == kWarpGateLaneE) { X.r -= fix.r; X.i -= fix.i; }
         }
         const double nrm = cnorm(X);
@@ -186,29 +145,116 @@ demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         const double eE1 = __shfl_sync(kFull, nrm, kWarpGateLaneE), eL1 = __shfl_sync(kFull, nrm, kWarpGateLaneL);
         const double eE2 = __shfl_sync(kFull, nrm, 16 + kWarpGateLaneE), eL2 = __shfl_sync(kFull, nrm, 16 + kWarpGateLaneL);
         bool tone1;
-        const double soft = warp_uniform_timing(e1, e2, eE1, eL1, eE2, eL2, timing_freq, pos, tone1);
+        const double soft = warp_uniform_timing(e1, e2, eE1, eL1, eE2, eL2, timing_freq, pos, tone1, K);
+        if (lane == 0) *soft_ptr = soft;
+        ++soft_ptr;
+
+        // ---- next symbol's samples (its window is already in the ring, see ring_maintain)
+        const int b_next = __double2int_rz(pos);  // pos >= 0: truncation == floor (:125)
+        load_window(b_next, s5);
 
         // ---- AFC on the on-time gate lanes (:289-307)
-        cplx Ou;
-        const double pd_own = warp_lane_afc_phase(wl, X, ph_own, first, Ou);
-        const cplx z40 = shfl_c(wl.R, tone_base | kWarpLaneZ40);
-        wl.prev = cmul(Ou, cconj(z40));  // :309-310, pre-rotated to the next symbol's phase frame
-        ph_own = wrap_phase(fma(40.0, wl.inc, ph_own));  // :250-262
-        if (!first) {
+        const bool x_zero = nrm == 0.0;
+        double pd_own = 0.0;
+        if (!FIRST) pd_own = warp_lane_afc_phase(wl, X, RP, x_zero || prev_zero, ph_own, K);
+        const cplx z50 = shfl_c(wl.R, tone_base | 10);   // R of lane p = 10 is z^50 = z^10 * z^40
+        wl.prev = cmul(X, cconj(z50));                    // :309-310, pre-rotated to the next symbol's phase frame
+        prev_zero = x_zero;
+        ph_own = warp_wrap_phase(fma(40.0, wl.inc, ph_own), K);   // :250-262
+        if (!FIRST) {
             const double pd = __shfl_sync(kFull, pd_own, tone1 ? kWarpGateLaneO : 16 + kWarpGateLaneO);
-            afc_loop(freq_offset, pd, afc_alpha);
-            warp_lane_lo(wl, freq_offset);
+            warp_afc_loop(freq_offset, pd, afc_alpha, K);
+            warp_lane_lo_fast(wl, freq_offset, K);
         }
-        if (lane == 0) soft_row[n_sym] = soft;
-        ++n_sym;
-        ++sym_in_call;
+        RP = cmul(wl.R, wl.prev);
+        return b_next;
+    }
+};
+
+}  // namespace
+
+__global__ void __launch_bounds__(32)
+demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
+                  int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
+    __shared__ __align__(128) uint32_t ring_sm[kRingWords];
+    __shared__ __align__(8) unsigned long long mbar_sm[kNumSlots];
+    const int lane = threadIdx.x;
+    const int stream = blockIdx.x;
+
+    WarpCtx c;
+    c.K = load_table_pinned();
+    c.lane = lane;
+    c.ring = ring_sm;
+    c.ring_s = smem_u32(ring_sm);
+    c.mbar_s = smem_u32(mbar_sm);
+    if (lane == 0) {
+#pragma unroll
+        for (int p = 0; p < kNumSlots; ++p) mbar_init(c.mbar_s + 8 * p, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+
+    DemodState st = dstate[stream];
+    const long long avail = sb.avail[stream];
+    const long long row0 = sb.row_base;
+    c.row = sb.iq + (long long)stream * sb.stride;  // row[r] holds absolute sample row0 + r
+    c.stride_i = (int)sb.stride;
+    c.avail_rel = (int)(avail - row0);
+    double* const soft_row = so.soft + (long long)stream * so.stride - so.base;
+    c.soft_ptr = soft_row + st.n_sym;
+    c.afc_alpha = afc_alpha;
+
+    warp_lane_init(c.wl, lane, c.K);
+    warp_lane_lo(c.wl, st.freq_offset);  // general version: a -o offset may exceed the fast range
+    c.wl.prev = c.wl.tone ? st.p2 : st.p1;
+    c.prev_zero = c.wl.prev.r == 0.0 && c.wl.prev.i == 0.0;
+    c.RP = cmul(c.wl.R, c.wl.prev);
+    c.lane_slot = 5 * (c.wl.p > 12 ? 12 : c.wl.p);
+    c.tone_base = lane & 16;
+    c.freq_offset = st.freq_offset;
+    c.pos = st.pos;
+    c.timing_freq = st.timing_freq;
+    c.ph_own = c.wl.tone ? st.ph2 : st.ph1;  // this lane's tone's absolute LO phase
+    c.first_s = -1;
+    c.issued_s = c.ready_s = 0;
+
+    const long long n_sym0 = st.n_sym, origin0 = st.origin;
+    for (;;) {
+        // ---- call boundary (warp-uniform slow path): close / open demodulate() calls (:1012-1113)
+        st.n_sym = n_sym0 + (long long)(c.soft_ptr - (soft_row + n_sym0));
+        if (!demod_schedule(st, c.pos, mode, avail, final_flag != 0)) break;
+        c.origin_rel = (int)(st.origin - row0);
+        const int call_len_i = (int)st.call_len;
+        const double call_len_d = (double)st.call_len;
+        int b = __double2int_rz(c.pos);  // pos >= 0: truncation == floor (:125)
+        if (c.first_s < 0) {  // first symbol of this launch: prime the ring
+            const int w0 = c.origin_rel + b - kWinLead;
+            c.first_s = w0 < 0 ? 0 : (w0 & ~(kSlotSamples - 1));
+            c.issued_s = c.ready_s = c.first_s;
+        }
+        uint32_t s5[5];
+        c.ring_maintain(c.origin_rel + b - kWinLead);
+        c.load_window(b, s5);
+        if (st.sym_in_call == 0) {
+            b = c.symbol<true>(b, s5);
+            st.sym_in_call = 1;
+            if (!((c.pos + 40.0) + 10.0 < call_len_d)) continue;
+        }
+        // ---- hot loop: while (pos + 50 < N) (:221); the integer test is a conservative shortcut
+        for (;;) {
+            if (b + 52 >= call_len_i && !((c.pos + 40.0) + 10.0 < call_len_d)) break;
+            c.ring_maintain(c.origin_rel + b - kWinLead);
+            b = c.symbol<false>(b, s5);
+        }
+        st.sym_in_call = 2;  // any non-zero value: the open call has produced symbols
     }
 
     // persist the stream's state
-    const double ph1 = __shfl_sync(kFull, ph_own, 0), ph2 = __shfl_sync(kFull, ph_own, 16);
-    const cplx p1 = shfl_c(wl.prev, kWarpGateLaneO), p2 = shfl_c(wl.prev, 16 + kWarpGateLaneO);
+    const double ph1 = __shfl_sync(kFull, c.ph_own, 0), ph2 = __shfl_sync(kFull, c.ph_own, 16);
+    const cplx p1 = shfl_c(c.wl.prev, kWarpGateLaneO), p2 = shfl_c(c.wl.prev, 16 + kWarpGateLaneO);
     if (lane == 0) {
-        st.freq_offset = freq_offset; st.pos = pos; st.timing_freq = timing_freq;
+        st.freq_offset = c.freq_offset; st.pos = c.pos; st.timing_freq = c.timing_freq;
         st.ph1 = ph1; st.ph2 = ph2; st.p1 = p1; st.p2 = p2;
         dstate[stream] = st;
         unsigned long long dsym = (unsigned long long)(st.n_sym - n_sym0);
@@ -222,9 +268,7 @@ demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
 cudaError_t launch_demod_warp(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                               cudaStream_t st) {
-    const int grid = (n_streams + kWarpsPerCta - 1) / kWarpsPerCta;
-    demod_warp_kernel<<<grid, 32 * kWarpsPerCta, 0, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha,
-                                                           counters);
+    demod_warp_kernel<<<n_streams, 32, 0, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
     return cudaGetLastError();
 }
 

@@ -10,9 +10,11 @@
 #if defined(__CUDACC__)
 #define OPVD_HD __host__ __device__ __forceinline__
 #define OPVD_D __device__ __forceinline__
+#define OPVD_HD_COLD __host__ __device__ __noinline__
 #else
 #define OPVD_HD inline
 #define OPVD_D inline
+#define OPVD_HD_COLD inline
 #endif
 
 namespace opvd {

@@ -98,9 +98,15 @@ size_t hostsim_demod_warp(const int16_t* iq, size_t n, int mode, double afc_alph
 
     WarpLane wl[32];
     for (int l = 0; l < 32; ++l) {
-        warp_lane_init(wl[l], l);
+        warp_lane_init(wl[l], l, g_fm);
         warp_lane_lo(wl[l], st.freq_offset);
         wl[l].prev = wl[l].tone ? st.p2 : st.p1;
+    }
+    cplx RP[32];
+    bool prev_zero[32];
+    for (int l = 0; l < 32; ++l) {
+        RP[l] = cmul(wl[l].R, wl[l].prev);
+        prev_zero[l] = wl[l].prev.r == 0.0 && wl[l].prev.i == 0.0;
     }
     double freq_offset = st.freq_offset, pos = st.pos, timing_freq = st.timing_freq, ph1 = st.ph1, ph2 = st.ph2;
     auto down = [](const cplx* v, int l, int d) { return (l + d < 32) ? v[l + d] : v[l]; };
@@ -110,7 +116,7 @@ size_t hostsim_demod_warp(const int16_t* iq, size_t n, int mode, double afc_alph
         const double f = pos - (double)b;
         const uint32_t* win = base + st.origin + b - kWinLead;
         const bool first = st.sym_in_call == 0;
-        cplx W[32], F[32], A[32], B[32], Cc[32], X[32], Ou[32];
+        cplx W[32], F[32], A[32], B[32], Cc[32], X[32];
         double nrm[32], pdo[32];
         for (int l = 0; l < 32; ++l) {
             const int pc = wl[l].p > 12 ? 12 : wl[l].p;
@@ -132,13 +138,18 @@ size_t hostsim_demod_warp(const int16_t* iq, size_t n, int mode, double afc_alph
         }
         for (int l = 0; l < 32; ++l) nrm[l] = cnorm(X[l]);
         bool tone1;
-        const double soft = warp_uniform_timing(nrm[2], nrm[18], nrm[0], nrm[4], nrm[16], nrm[20], timing_freq, pos, tone1);
-        for (int l = 0; l < 32; ++l) pdo[l] = warp_lane_afc_phase(wl[l], X[l], wl[l].tone ? ph2 : ph1, first, Ou[l]);
-        if (!first) afc_loop(freq_offset, pdo[tone1 ? 2 : 18], afc_alpha);
-        for (int l = 0; l < 32; ++l) wl[l].prev = cmul(Ou[l], cconj(wl[(l & 16) | kWarpLaneZ40].R));
-        ph1 = wrap_phase(fma(40.0, wl[0].inc, ph1));
-        ph2 = wrap_phase(fma(40.0, wl[16].inc, ph2));
-        if (!first) for (int l = 0; l < 32; ++l) warp_lane_lo(wl[l], freq_offset);
+        const double soft = warp_uniform_timing(nrm[2], nrm[18], nrm[0], nrm[4], nrm[16], nrm[20], timing_freq, pos, tone1, g_fm);
+        for (int l = 0; l < 32; ++l) {
+            const bool xz = nrm[l] == 0.0;
+            pdo[l] = first ? 0.0 : warp_lane_afc_phase(wl[l], X[l], RP[l], xz || prev_zero[l], wl[l].tone ? ph2 : ph1, g_fm);
+            prev_zero[l] = xz;
+        }
+        if (!first) warp_afc_loop(freq_offset, pdo[tone1 ? 2 : 18], afc_alpha, g_fm);
+        for (int l = 0; l < 32; ++l) wl[l].prev = cmul(X[l], cconj(wl[(l & 16) | 10].R));
+        ph1 = warp_wrap_phase(fma(40.0, wl[0].inc, ph1), g_fm);
+        ph2 = warp_wrap_phase(fma(40.0, wl[16].inc, ph2), g_fm);
+        if (!first) for (int l = 0; l < 32; ++l) warp_lane_lo_fast(wl[l], freq_offset, g_fm);
+        for (int l = 0; l < 32; ++l) RP[l] = cmul(wl[l].R, wl[l].prev);
         st.sym_in_call++;
         if (ns < cap) soft_out[ns] = soft;
         ++ns;
