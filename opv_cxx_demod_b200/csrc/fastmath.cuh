@@ -27,6 +27,7 @@ struct FastMathTable {
     double two_pi_over_fs, inc_dev, sym_rate_over_two_pi, two_pi, inv_two_pi;
     double eps_ted, k_tf, k_adj, lim_tf;  // 1e-10 (:280), 0.00001 (:283), 0.005 (:285), 0.1 (:284)
     double tau_c, tau_s;                  // cos, sin of 2*pi/160 (tone step)
+    double pi_4;
 };
 
 #define OPVD_FASTMATH_TABLE_INIT                                                                          \
@@ -39,20 +40,14 @@ struct FastMathTable {
          -1.0 / 87178291200.0},                                                                           \
         0.41421356237309504880,                                                                           \
         2.8981482044186284e-06, 0.039269908169872414, 8626.197915580728, 6.283185307179586,               \
-        0.15915494309189535, 1e-10, 0.00001, 0.005, 0.1, 0.9992290362407229, 0.03925981575906861        \
+        0.15915494309189535, 1e-10, 0.00001, 0.005, 0.1, 0.9992290362407229, 0.03925981575906861,       \
+        0.78539816339744830962                                                                            \
     }
-
-// octant offsets of atan2_fast, index = big | swap << 1 | (x < 0) << 2 (dynamically indexed: stays in memory)
-#define OPVD_ATAN_BASE_INIT                                                                           \
-    {0.0, 0.78539816339744830962, 1.57079632679489661923, 0.78539816339744830962,                     \
-     3.14159265358979323846, 2.35619449019234492885, 1.57079632679489661923, 2.35619449019234492885}
 
 #if defined(__CUDACC__)
 static __constant__ FastMathTable g_fm = OPVD_FASTMATH_TABLE_INIT;
-static __constant__ double g_atan_base[8] = OPVD_ATAN_BASE_INIT;
 #else
 static const FastMathTable g_fm = OPVD_FASTMATH_TABLE_INIT;
-static const double g_atan_base[8] = OPVD_ATAN_BASE_INIT;
 #endif
 
 // Register-resident copy of the table for a long-running loop.  ptxas re-materialises values it can
@@ -124,9 +119,13 @@ OPVD_HD double atan2_fast(double y, double x, const FastMathTable& K) {
     const double q0 = fma(u2, p23, p01), q1 = fma(u2, p67, p45), q2 = fma(u2, pab, p89);
     const double P = fma(u4, fma(u4, q2, q1), q0);
     const double a0 = fma(t * u, P, t);
+    // undo the reductions: a = m*pi/4 +/- a0 with m = big, then 2-m if swapped, then 4-m if x < 0
+    // (integer selects, off the critical path; an indexed constant load here stalled the warp ~8 %)
     const bool xneg = x < 0.0;
-    const int idx = (big ? 1 : 0) | (swap ? 2 : 0) | (xneg ? 4 : 0);
-    const double a = g_atan_base[idx] + flip_sign_if(a0, (big != swap) != xneg);
+    int m = big ? 1 : 0;
+    m = swap ? 2 - m : m;
+    m = xneg ? 4 - m : m;
+    const double a = fma((double)m, K.pi_4, flip_sign_if(a0, (big != swap) != xneg));
     return copysign(a, y);
 }
 

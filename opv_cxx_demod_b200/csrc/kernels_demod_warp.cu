@@ -105,6 +105,9 @@ struct WarpCtx {
         while (w0 + (kNumSlots - 1) * kSlotSamples >= issued_s && issued_s < avail_rel) {
             __syncwarp();  // every lane is done with the slot about to be recycled
             issue_slot();
+            // the absolute LO phase is only read in the signed-zero corner: advance it unwrapped in
+            // the symbol loop and wrap it here, every ~1.6 symbols (|ph| stays < 10 rad)
+            ph_own = warp_wrap_phase(ph_own, K);
         }
         while (w0 + kLookahead >= ready_s && ready_s < issued_s) wait_slot();
     }
@@ -160,7 +163,7 @@ struct WarpCtx {
         const cplx z50 = shfl_c(wl.R, tone_base | 10);   // R of lane p = 10 is z^50 = z^10 * z^40
         wl.prev = cmul(X, cconj(z50));                    // :309-310, pre-rotated to the next symbol's phase frame
         prev_zero = x_zero;
-        ph_own = warp_wrap_phase(fma(40.0, wl.inc, ph_own), K);   // :250-262
+        ph_own = fma(40.0, wl.inc, ph_own);               // :250-262 (wrapped in ring_maintain)
         if (!FIRST) {
             const double pd = __shfl_sync(kFull, pd_own, tone1 ? kWarpGateLaneO : 16 + kWarpGateLaneO);
             warp_afc_loop(freq_offset, pd, afc_alpha, K);
@@ -251,6 +254,7 @@ demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     }
 
     // persist the stream's state
+    c.ph_own = warp_wrap_phase(c.ph_own, c.K);
     const double ph1 = __shfl_sync(kFull, c.ph_own, 0), ph2 = __shfl_sync(kFull, c.ph_own, 16);
     const cplx p1 = shfl_c(c.wl.prev, kWarpGateLaneO), p2 = shfl_c(c.wl.prev, 16 + kWarpGateLaneO);
     if (lane == 0) {

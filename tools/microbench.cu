@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdint>
+#include <cstring>
 
 template <int OP>
 __global__ void k(unsigned long long* out, int iters, double seed) {
@@ -60,6 +61,30 @@ __global__ void k(unsigned long long* out, int iters, double seed) {
         }
         double s = 0; for (int i = 0; i < 8; ++i) s += a[i];
         if (s == 12345.678) out[0] = 1;
+    } else if (OP == 7) {  // magic-number int16 -> double (PRMT/LOP + DADD), same harness as OP 6
+        double a[8];
+        unsigned w = (unsigned)seed * 2654435761u + tid;
+        for (int i = 0; i < 8; ++i) a[i] = 0.0;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const unsigned h = ((w >> ((i & 1) * 16)) & 0xFFFFu) ^ 0x8000u;
+                a[i] += __hiloint2double(0x43300000, (int)h) - 4503599627403264.0;
+                w = w * 1664525u + 1013904223u;
+            }
+        }
+        double s = 0; for (int i = 0; i < 8; ++i) s += a[i];
+        if (s == 12345.678) out[0] = 1;
+    } else if (OP == 8) {  // accuracy of the MUFU.RCP64H seed: max |1 - b*r| over a sweep, stored as bits
+        double worst = 0.0;
+        for (int it = 0; it < iters; ++it) {
+            const double b = 1.0 + (double)((tid * 7919u + it * 104729u) & 0xFFFFFu) / 1048576.0 + 1e-9 * it;
+            double r;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+            const double e = fabs(fma(-b, r, 1.0));
+            worst = e > worst ? e : worst;
+        }
+        atomicMax(out, (unsigned long long)__double_as_longlong(worst));
     } else if (OP == 5) {  // dependent DFMA chain: latency
         double a = seed + tid;
         for (int it = 0; it < iters * 8; ++it) a = fma(a, 1.0000001, 1e-9);
@@ -89,11 +114,20 @@ int main() {
            dpx = run<3>(grid, block, iters, 8), shfl = run<4>(grid, block, iters, 4), i2f = run<6>(grid, block, iters, 8);
     // latency: one warp per SM
     double chain = run<5>(sms, 32, 4000, 8);  // dependent ops/s over sms*32 threads
+    double magic = run<7>(grid, block, iters, 8);
+    double rcp_err;
+    {
+        unsigned long long* d; cudaMalloc(&d, 8); cudaMemset(d, 0, 8);
+        k<8><<<grid, block>>>(d, 2000, 1.0);
+        unsigned long long bits; cudaMemcpy(&bits, d, 8, cudaMemcpyDeviceToHost); cudaFree(d);
+        memcpy(&rcp_err, &bits, 8);
+    }
     int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz_max\": %d, \"dfma_per_s\": %.4g, \"fp64_tflops\": %.3f, "
            "\"ffma_per_s\": %.4g, \"fp32_tflops\": %.3f, \"alu_ops_per_s\": %.4g, \"dpx_vibmin_add_per_s\": %.4g, "
-           "\"shfl_per_s\": %.4g, \"i2f_f64_s16_plus_dadd_per_s\": %.4g, \"dfma_dependent_ns\": %.3f}\n",
-           p.name, sms, clk, dfma, 2 * dfma / 1e12, ffma, 2 * ffma / 1e12, alu, dpx, shfl, i2f,
+           "\"shfl_per_s\": %.4g, \"i2f_f64_s16_plus_dadd_per_s\": %.4g, \"magic_cvt_plus_dadd_per_s\": %.4g, "
+           "\"rcp64h_seed_max_rel_err\": %.3g, \"dfma_dependent_ns\": %.3f}\n",
+           p.name, sms, clk, dfma, 2 * dfma / 1e12, ffma, 2 * ffma / 1e12, alu, dpx, shfl, i2f, magic, rcp_err,
            1e9 / (chain / (sms * 32.0)));
     return 0;
 }
