@@ -1,0 +1,142 @@
+// demod_batch_core.cuh — arithmetic of the BATCHED demodulator (kernels_demod_batch.cu): a CTA owns 32
+// streams; every symbol is split into a parallel window phase (four helper threads per stream: one
+// tone x one half of the 60-sample window each) and a serial loop phase (one lane per stream).
+// Same algorithm as demod_core.cuh (reference: MSKDemodulatorAFC::demodulate,
+// /root/reference/src/opv-demod.cpp:206-329).  Host/device code: the CUDA kernel and the CPU
+// host-sim test (tests/hostsim) compile exactly these functions.
+//
+// Window slots k = 0..60 are the raw samples b-10 .. b+50; slot k carries the weight z^k inside a
+// 10-slot block and q = z^10 between blocks:
+//   H_m = sum_{j<10} s[10m+j] z^j                       block sums, m = 0..5   (Horner, helper threads)
+//   E = H0 + qH1 + q^2 H2 + q^3 H3,  O = H1 + .. + q^3 H4,  L = H2 + .. + q^3 H5
+// A helper owns blocks 3h..3h+2 (h = window half) and hands over three partial gates so that the
+// serial lane only needs three complex FMAs per tone:
+//   h = 0:  Ea = H0 + q(H1 + qH2),  Oa = H1 + qH2,  La = H2
+//   h = 1:  Eb = H3,  Ob = H3 + qH4,  Lb = H3 + q(H4 + qH5)
+//   E = Ea + q^3 Eb,   O = Oa + q^2 Ob,   L = La + q Lb
+#pragma once
+#include "demod_core.cuh"
+#include "fastmath.cuh"
+
+namespace opvd {
+
+struct HalfGates {
+    cplx E, O, L;
+};
+
+// Horner over 10 consecutive samples
+OPVD_HD cplx horner10(const double* I, const double* Q, cplx z) {
+    cplx g = {I[9], Q[9]};
+#pragma unroll
+    for (int r = 8; r >= 0; --r) {
+        const double nr = fma(g.r, z.r, fma(-g.i, z.i, I[r]));
+        const double ni = fma(g.r, z.i, fma(g.i, z.r, Q[r]));
+        g.r = nr; g.i = ni;
+    }
+    return g;
+}
+
+// one tone, one window half: I/Q = the half's 30 samples (slots 30h .. 30h+29)
+OPVD_HD HalfGates batch_half_gates(const double* I, const double* Q, cplx z, cplx q, int half) {
+    const cplx A = horner10(I, Q, z), B = horner10(I + 10, Q + 10, z), C = horner10(I + 20, Q + 20, z);
+    HalfGates o;
+    if (half == 0) {
+        o.L = C;
+        o.O = cfma(q, C, B);
+        o.E = cfma(q, o.O, A);
+    } else {
+        o.E = A;
+        o.O = cfma(q, B, A);
+        o.L = cfma(q, cfma(q, C, B), A);
+    }
+    return o;
+}
+
+// tone step z = exp(-j*inc_t) and block step q = z^10 from the AFC offset (:210-211, :305-306)
+struct ToneLo {
+    cplx z, q;
+    double inc;
+};
+OPVD_HD void batch_lo(double freq_offset, ToneLo& t1, ToneLo& t2) {
+    const LoSteps l = lo_steps(freq_offset);  // Taylor zeta, sincos fallback for huge -o offsets
+    t1.z = l.z1; t2.z = l.z2; t1.inc = l.inc1; t2.inc = l.inc2;
+    cplx a = csqr(l.z1), b = csqr(l.z2);      // z^2
+    cplx a4 = csqr(a), b4 = csqr(b);          // z^4
+    a = cmul(a4, l.z1); b = cmul(b4, l.z2);   // z^5
+    t1.q = csqr(a); t2.q = csqr(b);           // z^10
+}
+
+// serial lane: finish the three gates of one tone from the two half-window partials, apply the
+// post-sum linear interpolator (demod_core.cuh) and return the gate energies and the on-time sum.
+// sI/sQ: raw samples at window slots 0, 10, 20, 40, 50, 60.
+struct ToneGates {
+    cplx O;          // interpolated on-time correlation (common unit-modulus phase factor dropped)
+    double eE, eO, eL;
+    cplx z40;
+};
+OPVD_HD ToneGates batch_finish_tone(const HalfGates& a, const HalfGates& b, const ToneLo& t, double f,
+                                    const double* sI, const double* sQ, cplx fixE) {
+    const cplx q2 = csqr(t.q);
+    const cplx q3 = cmul(q2, t.q);
+    ToneGates o;
+    o.z40 = csqr(q2);
+    const cplx E = cfma(q3, b.E, a.E), O = cfma(q2, b.O, a.O), L = cfma(t.q, b.L, a.L);
+    const cplx dE = edge_term(sI[3], sQ[3], sI[0], sQ[0], o.z40);
+    const cplx dO = edge_term(sI[4], sQ[4], sI[1], sQ[1], o.z40);
+    const cplx dL = edge_term(sI[5], sQ[5], sI[2], sQ[2], o.z40);
+    // X = (1-f)*C + f*conj(z)*(C + dX) = C + f*(conj(z)*(C + dX) - C)
+    auto interp = [&](cplx C, cplx dX) {
+        const cplx S = {C.r + dX.r, C.i + dX.i};
+        const cplx T = {fma(t.z.r, S.r, t.z.i * S.i), fma(t.z.r, S.i, -(t.z.i * S.r))};
+        return cplx{fma(f, T.r - C.r, C.r), fma(f, T.i - C.i, C.i)};
+    };
+    cplx Ei = interp(E, dE);
+    const cplx Li = interp(L, dL);
+    Ei.r -= fixE.r; Ei.i -= fixE.i;  // early-gate clamp of the first symbol of a call (:237); zero otherwise
+    o.O = interp(O, dO);
+    o.eE = cnorm(Ei); o.eO = cnorm(o.O); o.eL = cnorm(Li);
+    return o;
+}
+
+// Loop-carried registers of one stream in the serial lane.
+struct BatchRegs {
+    double freq_offset, ph1, ph2, pos, timing_freq;
+    cplx p1, p2;
+    ToneLo t1, t2;
+};
+
+OPVD_HD double clamp_sym_b(double v, double lim) { return fabs(v) > lim ? copysign(lim, v) : v; }
+
+OPVD_HD_COLD double batch_afc_corner(cplx dom, cplx prev, double ph) { return afc_phase_signed_zero(dom, prev, ph); }
+
+// Serial part of one symbol (:264-313) given both tones' gates.  first_in_call: no AFC update (:289).
+// g1.E energy must already include the first-symbol early-gate correction when it applies.
+OPVD_HD double batch_symbol_serial(BatchRegs& r, const ToneGates& g1, const ToneGates& g2, bool first_in_call,
+                                   double afc_alpha, const FastMathTable& K) {
+    const double soft = g2.eO - g1.eO;     // :268
+    const bool tone1 = g1.eO > g2.eO;      // :272, :291
+    const double ee = tone1 ? g1.eE : g2.eE, el = tone1 ? g1.eL : g2.eL;
+    const double ted = div_fast(el - ee, el + ee + 1e-10);              // :280
+    r.timing_freq = clamp_sym_b(r.timing_freq + 0.00001 * ted, 0.1);    // :283-284
+    const double adj = clamp_sym_b(0.005 * ted + r.timing_freq, 2.0);   // :285-286
+    if (!first_in_call) {                                               // :289-307
+        const cplx dom = tone1 ? g1.O : g2.O, prev = tone1 ? r.p1 : r.p2;
+        const double xr = fma(dom.r, prev.r, dom.i * prev.i);
+        const double xi = fma(dom.i, prev.r, -(dom.r * prev.i));
+        double pd = atan2_fast(xi, xr, K);
+        const bool corner = (dom.r == 0.0 && dom.i == 0.0) || (prev.r == 0.0 && prev.i == 0.0);
+        if (corner) pd = batch_afc_corner(dom, prev, tone1 ? r.ph1 : r.ph2);
+        const double ferr = pd * kSymRateOverTwoPi;
+        r.freq_offset = clamp_sym_b(r.freq_offset + afc_alpha * ferr, 2000.0);
+    }
+    // previous correlations for the NEXT symbol, rotated to the phase frame at the next symbol start
+    r.p1 = cmul(g1.O, cconj(g1.z40));  // :309-310
+    r.p2 = cmul(g2.O, cconj(g2.z40));
+    r.ph1 = wrap_phase(fma(40.0, r.t1.inc, r.ph1));  // :250-262
+    r.ph2 = wrap_phase(fma(40.0, r.t2.inc, r.ph2));
+    if (!first_in_call) batch_lo(r.freq_offset, r.t1, r.t2);
+    r.pos += 40.0 + adj;  // :313
+    return soft;
+}
+
+}  // namespace opvd

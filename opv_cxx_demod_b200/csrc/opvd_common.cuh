@@ -10,11 +10,11 @@
 #if defined(__CUDACC__)
 #define OPVD_HD __host__ __device__ __forceinline__
 #define OPVD_D __device__ __forceinline__
-#define OPVD_HD_COLD __host__ __device__ __noinline__
+#define OPVD_HD_COLD static __host__ __device__ __noinline__
 #else
 #define OPVD_HD inline
 #define OPVD_D inline
-#define OPVD_HD_COLD inline
+#define OPVD_HD_COLD static inline
 #endif
 
 namespace opvd {

@@ -50,7 +50,9 @@ struct SoftBuffers {
 void launch_estimate(const StreamBuffers& sb, DemodState* dstate, double* est_out, int n_streams, int mode,
                      int final_flag, cudaStream_t st);
 
-// lanes_per_stream in {1, 2, 4, 32}; 0 = chosen from the stream count; returns cudaError
+// lanes_per_stream in {1, 2, 4, 32, 64}; 0 = chosen from the stream count; returns cudaError
+//   1/2/4  lane kernels (kernels_demod.cu)    32  warp per stream (kernels_demod_warp.cu)
+//   64     batched: 32 streams per 128-thread CTA (kernels_demod_batch.cu)
 cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                          int mode, int final_flag, double afc_alpha, int lanes_per_stream,
                          unsigned long long* counters, cudaStream_t st);
@@ -59,6 +61,11 @@ cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodSt
 cudaError_t launch_demod_warp(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                               cudaStream_t st);
+
+// batched variant (kernels_demod_batch.cu); selected by launch_demod for lanes_per_stream == 64
+cudaError_t launch_demod_batch(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
+                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
+                               cudaStream_t st);
 
 void launch_track(const SoftBuffers& so, const DemodState* dstate, TrackState* tstate, int n_streams,
                   FrameRec* frec, int max_frames, TrackEvent* events, int32_t* n_events, int max_events,
