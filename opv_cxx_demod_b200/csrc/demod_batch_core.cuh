@@ -14,6 +14,10 @@
 //   h = 0:  Ea = H0 + q(H1 + qH2),  Oa = H1 + qH2,  La = H2
 //   h = 1:  Eb = H3,  Ob = H3 + qH4,  Lb = H3 + q(H4 + qH5)
 //   E = Ea + q^3 Eb,   O = Oa + q^2 Ob,   L = La + q Lb
+// The post-sum linear interpolator X = C + f*(conj(z)*(C + dX) - C) (demod_core.cuh) is linear in the
+// gate sum C and its shifted-window edge term dX = s[last+1] z^40 - s[first], and both split over the
+// halves with the same weights (dE = -s0 + q^3 (s40 q), dO = -s10 + q^2 (s50 q^2), dL = -s20 + q (s60 q^3)),
+// so each helper interpolates its own partial gates and the serial lane combines finished values.
 #pragma once
 #include "demod_core.cuh"
 #include "fastmath.cuh"
@@ -36,19 +40,39 @@ OPVD_HD cplx horner10(const double* I, const double* Q, cplx z) {
     return g;
 }
 
-// one tone, one window half: I/Q = the half's 30 samples (slots 30h .. 30h+29)
-OPVD_HD HalfGates batch_half_gates(const double* I, const double* Q, cplx z, cplx q, int half) {
+// one tone, one window half: I/Q = the half's 30 samples (slots 30h .. 30h+29) plus, for h = 1,
+// slot 60 in I[30]/Q[30].  Returns the interpolated partial gates.
+OPVD_HD HalfGates batch_half_gates(const double* I, const double* Q, cplx z, cplx q, double f, int half) {
     const cplx A = horner10(I, Q, z), B = horner10(I + 10, Q + 10, z), C = horner10(I + 20, Q + 20, z);
-    HalfGates o;
+    HalfGates g, d;  // partial gate sums and their edge terms
     if (half == 0) {
-        o.L = C;
-        o.O = cfma(q, C, B);
-        o.E = cfma(q, o.O, A);
+        g.L = C;
+        g.O = cfma(q, C, B);
+        g.E = cfma(q, g.O, A);
+        d.E = {-I[0], -Q[0]};
+        d.O = {-I[10], -Q[10]};
+        d.L = {-I[20], -Q[20]};
     } else {
-        o.E = A;
-        o.O = cfma(q, B, A);
-        o.L = cfma(q, cfma(q, C, B), A);
+        g.E = A;
+        g.O = cfma(q, B, A);
+        g.L = cfma(q, cfma(q, C, B), A);
+        const cplx q2 = csqr(q), q3 = cmul(q2, q);
+        d.E = {q.r * I[10], q.i * I[10]};
+        d.E = {fma(-q.i, Q[10], d.E.r), fma(q.r, Q[10], d.E.i)};     // s40 * q
+        d.O = {q2.r * I[20], q2.i * I[20]};
+        d.O = {fma(-q2.i, Q[20], d.O.r), fma(q2.r, Q[20], d.O.i)};   // s50 * q^2
+        d.L = {q3.r * I[30], q3.i * I[30]};
+        d.L = {fma(-q3.i, Q[30], d.L.r), fma(q3.r, Q[30], d.L.i)};   // s60 * q^3
     }
+    auto interp = [&](cplx Cg, cplx dX) {
+        const cplx S = {Cg.r + dX.r, Cg.i + dX.i};
+        const cplx T = {fma(z.r, S.r, z.i * S.i), fma(z.r, S.i, -(z.i * S.r))};  // conj(z) * S
+        return cplx{fma(f, T.r - Cg.r, Cg.r), fma(f, T.i - Cg.i, Cg.i)};
+    };
+    HalfGates o;
+    o.E = interp(g.E, d.E);
+    o.O = interp(g.O, d.O);
+    o.L = interp(g.L, d.L);
     return o;
 }
 
@@ -66,35 +90,37 @@ OPVD_HD void batch_lo(double freq_offset, ToneLo& t1, ToneLo& t2) {
     t1.q = csqr(a); t2.q = csqr(b);           // z^10
 }
 
-// serial lane: finish the three gates of one tone from the two half-window partials, apply the
-// post-sum linear interpolator (demod_core.cuh) and return the gate energies and the on-time sum.
-// sI/sQ: raw samples at window slots 0, 10, 20, 40, 50, 60.
+// LO steps in the hot loop: valid for |freq_offset| <= 2.5 kHz, which the AFC clamp (:303) guarantees
+// after every update; coefficients come from the constant table (no FP64 immediates in the loop).
+OPVD_HD void batch_lo_fast(double freq_offset, ToneLo& t1, ToneLo& t2, const FastMathTable& K) {
+    const double d = freq_offset * K.two_pi_over_fs;
+    const cplx zeta = expmj_small(d, K);
+    t1.inc = d - K.inc_dev; t2.inc = d + K.inc_dev;
+    t1.z = cmul(cplx{K.tau_c, K.tau_s}, zeta);    // exp(+j*2pi/160) * exp(-j*delta)
+    t2.z = cmul(cplx{K.tau_c, -K.tau_s}, zeta);
+    cplx a = csqr(t1.z), b = csqr(t2.z);      // z^2
+    const cplx a4 = csqr(a), b4 = csqr(b);    // z^4
+    a = cmul(a4, t1.z); b = cmul(b4, t2.z);   // z^5
+    t1.q = csqr(a); t2.q = csqr(b);           // z^10
+}
+
+// Serial lane: combine the two halves' interpolated partial gates of one tone; returns the gate
+// energies, the on-time sum and z^40 (for the AFC's previous-correlation rotation).
 struct ToneGates {
     cplx O;          // interpolated on-time correlation (common unit-modulus phase factor dropped)
     double eE, eO, eL;
     cplx z40;
 };
-OPVD_HD ToneGates batch_finish_tone(const HalfGates& a, const HalfGates& b, const ToneLo& t, double f,
-                                    const double* sI, const double* sQ, cplx fixE) {
+OPVD_HD ToneGates batch_finish_tone(const HalfGates& a, const HalfGates& b, const ToneLo& t, cplx fixE) {
     const cplx q2 = csqr(t.q);
     const cplx q3 = cmul(q2, t.q);
     ToneGates o;
     o.z40 = csqr(q2);
-    const cplx E = cfma(q3, b.E, a.E), O = cfma(q2, b.O, a.O), L = cfma(t.q, b.L, a.L);
-    const cplx dE = edge_term(sI[3], sQ[3], sI[0], sQ[0], o.z40);
-    const cplx dO = edge_term(sI[4], sQ[4], sI[1], sQ[1], o.z40);
-    const cplx dL = edge_term(sI[5], sQ[5], sI[2], sQ[2], o.z40);
-    // X = (1-f)*C + f*conj(z)*(C + dX) = C + f*(conj(z)*(C + dX) - C)
-    auto interp = [&](cplx C, cplx dX) {
-        const cplx S = {C.r + dX.r, C.i + dX.i};
-        const cplx T = {fma(t.z.r, S.r, t.z.i * S.i), fma(t.z.r, S.i, -(t.z.i * S.r))};
-        return cplx{fma(f, T.r - C.r, C.r), fma(f, T.i - C.i, C.i)};
-    };
-    cplx Ei = interp(E, dE);
-    const cplx Li = interp(L, dL);
-    Ei.r -= fixE.r; Ei.i -= fixE.i;  // early-gate clamp of the first symbol of a call (:237); zero otherwise
-    o.O = interp(O, dO);
-    o.eE = cnorm(Ei); o.eO = cnorm(o.O); o.eL = cnorm(Li);
+    cplx E = cfma(q3, b.E, a.E);
+    const cplx L = cfma(t.q, b.L, a.L);
+    o.O = cfma(q2, b.O, a.O);
+    E.r -= fixE.r; E.i -= fixE.i;  // early-gate clamp of the first symbol of a call (:237); zero otherwise
+    o.eE = cnorm(E); o.eO = cnorm(o.O); o.eL = cnorm(L);
     return o;
 }
 
@@ -116,9 +142,9 @@ OPVD_HD double batch_symbol_serial(BatchRegs& r, const ToneGates& g1, const Tone
     const double soft = g2.eO - g1.eO;     // :268
     const bool tone1 = g1.eO > g2.eO;      // :272, :291
     const double ee = tone1 ? g1.eE : g2.eE, el = tone1 ? g1.eL : g2.eL;
-    const double ted = div_fast(el - ee, el + ee + 1e-10);              // :280
-    r.timing_freq = clamp_sym_b(r.timing_freq + 0.00001 * ted, 0.1);    // :283-284
-    const double adj = clamp_sym_b(0.005 * ted + r.timing_freq, 2.0);   // :285-286
+    const double ted = div_fast(el - ee, el + ee + K.eps_ted);               // :280
+    r.timing_freq = clamp_sym_b(r.timing_freq + K.k_tf * ted, K.lim_tf);     // :283-284
+    const double adj = clamp_sym_b(K.k_adj * ted + r.timing_freq, 2.0);      // :285-286
     if (!first_in_call) {                                               // :289-307
         const cplx dom = tone1 ? g1.O : g2.O, prev = tone1 ? r.p1 : r.p2;
         const double xr = fma(dom.r, prev.r, dom.i * prev.i);
@@ -126,15 +152,15 @@ OPVD_HD double batch_symbol_serial(BatchRegs& r, const ToneGates& g1, const Tone
         double pd = atan2_fast(xi, xr, K);
         const bool corner = (dom.r == 0.0 && dom.i == 0.0) || (prev.r == 0.0 && prev.i == 0.0);
         if (corner) pd = batch_afc_corner(dom, prev, tone1 ? r.ph1 : r.ph2);
-        const double ferr = pd * kSymRateOverTwoPi;
+        const double ferr = pd * K.sym_rate_over_two_pi;
         r.freq_offset = clamp_sym_b(r.freq_offset + afc_alpha * ferr, 2000.0);
     }
     // previous correlations for the NEXT symbol, rotated to the phase frame at the next symbol start
     r.p1 = cmul(g1.O, cconj(g1.z40));  // :309-310
     r.p2 = cmul(g2.O, cconj(g2.z40));
-    r.ph1 = wrap_phase(fma(40.0, r.t1.inc, r.ph1));  // :250-262
-    r.ph2 = wrap_phase(fma(40.0, r.t2.inc, r.ph2));
-    if (!first_in_call) batch_lo(r.freq_offset, r.t1, r.t2);
+    r.ph1 = fma(-K.two_pi, rint(fma(40.0, r.t1.inc, r.ph1) * K.inv_two_pi), fma(40.0, r.t1.inc, r.ph1));  // :250-262
+    r.ph2 = fma(-K.two_pi, rint(fma(40.0, r.t2.inc, r.ph2) * K.inv_two_pi), fma(40.0, r.t2.inc, r.ph2));
+    if (!first_in_call) batch_lo_fast(r.freq_offset, r.t1, r.t2, K);  // |freq_offset| <= 2 kHz after the clamp above
     r.pos += 40.0 + adj;  // :313
     return soft;
 }

@@ -197,18 +197,15 @@ size_t hostsim_demod_batch(const int16_t* iq, size_t n, int mode, double afc_alp
         HalfGates hg[2][2];
         for (int tone = 0; tone < 2; ++tone)
             for (int half = 0; half < 2; ++half) {
-                double I[30], Q[30];
-                for (int j = 0; j < 30; ++j) unpack_iq(win[30 * half + j], I[j], Q[j]);
+                double I[31], Q[31];
+                for (int j = 0; j < 31; ++j) unpack_iq(win[30 * half + j], I[j], Q[j]);
                 const ToneLo& t = tone ? r.t2 : r.t1;
-                hg[tone][half] = batch_half_gates(I, Q, t.z, t.q, half);
+                hg[tone][half] = batch_half_gates(I, Q, t.z, t.q, f, half);
             }
-        double sI[6], sQ[6];
-        const int slots[6] = {0, 10, 20, 40, 50, 60};
-        for (int k = 0; k < 6; ++k) unpack_iq(win[slots[k]], sI[k], sQ[k]);
         cplx fix1 = {0.0, 0.0}, fix2 = {0.0, 0.0};
         if (first) { fix1 = first_symbol_fix(win, f, r.t1.z); fix2 = first_symbol_fix(win, f, r.t2.z); }
-        const ToneGates g1 = batch_finish_tone(hg[0][0], hg[0][1], r.t1, f, sI, sQ, fix1);
-        const ToneGates g2 = batch_finish_tone(hg[1][0], hg[1][1], r.t2, f, sI, sQ, fix2);
+        const ToneGates g1 = batch_finish_tone(hg[0][0], hg[0][1], r.t1, fix1);
+        const ToneGates g2 = batch_finish_tone(hg[1][0], hg[1][1], r.t2, fix2);
         const double soft = batch_symbol_serial(r, g1, g2, first, afc_alpha, g_fm);
         st.sym_in_call++;
         if (ns < cap) soft_out[ns] = soft;
