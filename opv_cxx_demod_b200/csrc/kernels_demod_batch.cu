@@ -80,12 +80,16 @@ __device__ __forceinline__ void stage_load(const uint32_t* row, int idx, int str
 }
 
 // early-gate correction for the first symbol of a call, both tones (rare: kept out of line)
-__device__ __noinline__ void first_fix_cold(const uint32_t* win, double f, cplx z1, cplx z2, cplx& fix1, cplx& fix2) {
-    fix1 = first_symbol_fix_w([&](int kk) { return win[kk * kSpc]; }, f, z1);
-    fix2 = first_symbol_fix_w([&](int kk) { return win[kk * kSpc]; }, f, z2);
+__device__ __noinline__ cplx first_fix_cold(const uint32_t* win, double f, cplx z) {
+    return first_symbol_fix_w([&](int kk) { return win[kk * kSpc]; }, f, z);
 }
-__device__ __noinline__ bool schedule_cold(DemodState& st, double& pos, int mode, long long avail, bool final_flag) {
-    return demod_schedule(st, pos, mode, avail, final_flag);
+// call scheduling out of line.  Everything it touches by reference lives in local memory, so the
+// hot loop hands it copies: the position comes back through st.pos.
+__device__ __noinline__ bool schedule_cold(DemodState& st, int mode, long long avail, bool final_flag) {
+    double pos = st.pos;
+    const bool live = demod_schedule(st, pos, mode, avail, final_flag);
+    st.pos = pos;
+    return live;
 }
 
 __device__ __forceinline__ void publish_lo(BatchSmem& sm, int s, const BatchRegs& r) {
@@ -107,7 +111,8 @@ __device__ __forceinline__ void loop_warp(BatchSmem& sm, const StreamBuffers& sb
     r.p1 = st.p1; r.p2 = st.p2;
     batch_lo(r.freq_offset, r.t1, r.t2);  // general version: a -o offset may exceed the fast range
     const long long n_sym0 = st.n_sym, origin0 = st.origin;
-    bool live = valid && schedule_cold(st, r.pos, mode, avail, final_flag != 0);
+    bool live = valid && schedule_cold(st, mode, avail, final_flag != 0);
+    r.pos = st.pos;
     double call_len_d = (double)st.call_len, f = 0.0;
     int origin_rel = (int)(st.origin - row0);
     int w0 = 0;
@@ -135,19 +140,29 @@ __device__ __forceinline__ void loop_warp(BatchSmem& sm, const StreamBuffers& sb
         const bool first = sym_in_call == 0;
         __syncthreads();  // partial gates ready
         if (live) {
-            HalfGates a, b;
-            double2 v;
-            v = sm.part[0][0][s]; a.E = {v.x, v.y}; v = sm.part[0][1][s]; a.O = {v.x, v.y}; v = sm.part[0][2][s]; a.L = {v.x, v.y};
-            v = sm.part[1][0][s]; b.E = {v.x, v.y}; v = sm.part[1][1][s]; b.O = {v.x, v.y}; v = sm.part[1][2][s]; b.L = {v.x, v.y};
-            cplx fix1 = {0.0, 0.0}, fix2 = {0.0, 0.0};
-            if (first) {  // early-gate clamp (:237), once per call; window n is still in the ring
-                const uint32_t* win = &sm.ring[w0 & (kRingRows - 1)][s];
-                first_fix_cold(win, f, r.t1.z, r.t2.z, fix1, fix2);
+            // one tone at a time (the barrier keeps the second tone's loads from being hoisted, which
+            // would double the live registers)
+            const uint32_t* win = &sm.ring[w0 & (kRingRows - 1)][s];  // window n is still in the ring
+            ToneGates g1, g2;
+            {
+                HalfGates a, b;
+                double2 v;
+                v = sm.part[0][0][s]; a.E = {v.x, v.y}; v = sm.part[0][1][s]; a.O = {v.x, v.y}; v = sm.part[0][2][s]; a.L = {v.x, v.y};
+                v = sm.part[1][0][s]; b.E = {v.x, v.y}; v = sm.part[1][1][s]; b.O = {v.x, v.y}; v = sm.part[1][2][s]; b.L = {v.x, v.y};
+                cplx fix = {0.0, 0.0};
+                if (first) fix = first_fix_cold(win, f, r.t1.z);  // early-gate clamp (:237), once per call
+                g1 = batch_finish_tone(a, b, r.t1, fix);
             }
-            const ToneGates g1 = batch_finish_tone(a, b, r.t1, fix1);
-            v = sm.part[2][0][s]; a.E = {v.x, v.y}; v = sm.part[2][1][s]; a.O = {v.x, v.y}; v = sm.part[2][2][s]; a.L = {v.x, v.y};
-            v = sm.part[3][0][s]; b.E = {v.x, v.y}; v = sm.part[3][1][s]; b.O = {v.x, v.y}; v = sm.part[3][2][s]; b.L = {v.x, v.y};
-            const ToneGates g2 = batch_finish_tone(a, b, r.t2, fix2);
+            asm volatile("" ::: "memory");
+            {
+                HalfGates a, b;
+                double2 v;
+                v = sm.part[2][0][s]; a.E = {v.x, v.y}; v = sm.part[2][1][s]; a.O = {v.x, v.y}; v = sm.part[2][2][s]; a.L = {v.x, v.y};
+                v = sm.part[3][0][s]; b.E = {v.x, v.y}; v = sm.part[3][1][s]; b.O = {v.x, v.y}; v = sm.part[3][2][s]; b.L = {v.x, v.y};
+                cplx fix = {0.0, 0.0};
+                if (first) fix = first_fix_cold(win, f, r.t2.z);
+                g2 = batch_finish_tone(a, b, r.t2, fix);
+            }
             const double soft = batch_symbol_serial(r, g1, g2, first, afc_alpha, g_fm);
             *soft_ptr++ = soft;
             sym_in_call = 1;  // any non-zero value: the open call has produced symbols
@@ -155,7 +170,9 @@ __device__ __forceinline__ void loop_warp(BatchSmem& sm, const StreamBuffers& sb
             if (!((r.pos + 40.0) + 10.0 < call_len_d)) {  // :221 fails: close the call, maybe open the next
                 st.n_sym = (long long)(soft_ptr - soft_row);
                 st.sym_in_call = sym_in_call;
-                live = schedule_cold(st, r.pos, mode, avail, final_flag != 0);
+                st.pos = r.pos;
+                live = schedule_cold(st, mode, avail, final_flag != 0);
+                r.pos = st.pos;
                 sym_in_call = st.sym_in_call;
                 call_len_d = (double)st.call_len;
                 origin_rel = (int)(st.origin - row0);
@@ -225,7 +242,7 @@ __device__ __forceinline__ void helper_warp(BatchSmem& sm, const uint32_t* __res
             const uint32_t* src = &sm.ring[(w0 & (kRingRows - 1)) + 30 * half][s];
             double I[31], Q[31];  // slots 30h .. 30h+29, and slot 60 for the late gate's edge term (h = 1)
 #pragma unroll
-            for (int j = 0; j < 30; ++j) unpack_iq(src[j * kSpc], I[j], Q[j]);
+            for (int j = 0; j < 30; ++j) unpack_iq_mixed(src[j * kSpc], I[j], Q[j]);
             I[30] = 0.0; Q[30] = 0.0;
             if (half) unpack_iq(src[30 * kSpc], I[30], Q[30]);
             const cplx z = {sm.zq[tone][0][s], sm.zq[tone][1][s]}, q = {sm.zq[tone][2][s], sm.zq[tone][3][s]};

@@ -73,4 +73,16 @@ OPVD_HD void unpack_iq(uint32_t w, double& I, double& Q) {
 #endif
 }
 
+// Same values, conversions split over two pipes: I through I2F.F64.S16 (XU pipe, 8 cycles per warp
+// instruction), Q through the 2^52 bias trick (integer pipe + one DADD on the FP64 pipe).  A kernel
+// that converts 60 components per thread and symbol is otherwise bound by the XU pipe.
+OPVD_HD void unpack_iq_mixed(uint32_t w, double& I, double& Q) {
+#if defined(__CUDA_ARCH__)
+    I = (double)(int16_t)(w & 0xFFFFu);
+    Q = __hiloint2double(0x43300000, (int)((w >> 16) ^ 0x8000u)) - 4503599627403264.0;  // 2^52 + 2^15
+#else
+    unpack_iq(w, I, Q);
+#endif
+}
+
 }  // namespace opvd
