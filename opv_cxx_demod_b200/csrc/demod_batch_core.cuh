@@ -135,18 +135,33 @@ OPVD_HD double clamp_sym_b(double v, double lim) { return fabs(v) > lim ? copysi
 
 OPVD_HD_COLD double batch_afc_corner(cplx dom, cplx prev, double ph) { return afc_phase_signed_zero(dom, prev, ph); }
 
-// Serial part of one symbol (:264-313) given both tones' gates.  first_in_call: no AFC update (:289).
-// g1.E energy must already include the first-symbol early-gate correction when it applies.
-OPVD_HD double batch_symbol_serial(BatchRegs& r, const ToneGates& g1, const ToneGates& g2, bool first_in_call,
-                                   double afc_alpha, const FastMathTable& K) {
-    const double soft = g2.eO - g1.eO;     // :268
-    const bool tone1 = g1.eO > g2.eO;      // :272, :291
-    const double ee = tone1 ? g1.eE : g2.eE, el = tone1 ? g1.eL : g2.eL;
-    const double ted = div_fast(el - ee, el + ee + K.eps_ted);               // :280
-    r.timing_freq = clamp_sym_b(r.timing_freq + K.k_tf * ted, K.lim_tf);     // :283-284
-    const double adj = clamp_sym_b(K.k_adj * ted + r.timing_freq, 2.0);      // :285-286
+// The serial part of one symbol (:264-313) splits into two independent chains that the kernel runs on
+// two warps: the timing chain (soft decision, TED, timing loop -> pos) and the AFC chain (phase
+// detector, AFC loop, previous correlations, LO phases -> freq_offset).
+
+// timing chain (:264-286, :313); returns the soft symbol
+OPVD_HD double batch_timing(double eO1, double eO2, double eE1, double eL1, double eE2, double eL2,
+                            double& timing_freq, double& pos, const FastMathTable& K) {
+    const bool tone1 = eO1 > eO2;          // :272
+    const double ee = tone1 ? eE1 : eE2, el = tone1 ? eL1 : eL2;
+    const double ted = div_fast(el - ee, el + ee + K.eps_ted);           // :280
+    timing_freq = clamp_sym_b(timing_freq + K.k_tf * ted, K.lim_tf);     // :283-284
+    const double adj = clamp_sym_b(K.k_adj * ted + timing_freq, 2.0);    // :285-286
+    pos += 40.0 + adj;                                                   // :313
+    return eO2 - eO1;                                                    // :268
+}
+
+// AFC chain (:289-310, :250-262).  O1/O2: interpolated on-time sums, z40_t = z_t^40, inc_t = LO phase
+// steps used during this symbol.  first_in_call: no AFC update (:289).
+struct BatchAfc {
+    double freq_offset, ph1, ph2;
+    cplx p1, p2;
+};
+OPVD_HD void batch_afc(BatchAfc& r, cplx O1, cplx z40_1, double eO1, cplx O2, cplx z40_2, double eO2, double inc1,
+                       double inc2, bool first_in_call, double afc_alpha, const FastMathTable& K) {
     if (!first_in_call) {                                               // :289-307
-        const cplx dom = tone1 ? g1.O : g2.O, prev = tone1 ? r.p1 : r.p2;
+        const bool tone1 = eO1 > eO2;                                   // :291
+        const cplx dom = tone1 ? O1 : O2, prev = tone1 ? r.p1 : r.p2;
         const double xr = fma(dom.r, prev.r, dom.i * prev.i);
         const double xi = fma(dom.i, prev.r, -(dom.r * prev.i));
         double pd = atan2_fast(xi, xr, K);
@@ -156,12 +171,21 @@ OPVD_HD double batch_symbol_serial(BatchRegs& r, const ToneGates& g1, const Tone
         r.freq_offset = clamp_sym_b(r.freq_offset + afc_alpha * ferr, 2000.0);
     }
     // previous correlations for the NEXT symbol, rotated to the phase frame at the next symbol start
-    r.p1 = cmul(g1.O, cconj(g1.z40));  // :309-310
-    r.p2 = cmul(g2.O, cconj(g2.z40));
-    r.ph1 = fma(-K.two_pi, rint(fma(40.0, r.t1.inc, r.ph1) * K.inv_two_pi), fma(40.0, r.t1.inc, r.ph1));  // :250-262
-    r.ph2 = fma(-K.two_pi, rint(fma(40.0, r.t2.inc, r.ph2) * K.inv_two_pi), fma(40.0, r.t2.inc, r.ph2));
-    if (!first_in_call) batch_lo_fast(r.freq_offset, r.t1, r.t2, K);  // |freq_offset| <= 2 kHz after the clamp above
-    r.pos += 40.0 + adj;  // :313
+    r.p1 = cmul(O1, cconj(z40_1));  // :309-310
+    r.p2 = cmul(O2, cconj(z40_2));
+    const double a1 = fma(40.0, inc1, r.ph1), a2 = fma(40.0, inc2, r.ph2);  // :250-262
+    r.ph1 = fma(-K.two_pi, rint(a1 * K.inv_two_pi), a1);
+    r.ph2 = fma(-K.two_pi, rint(a2 * K.inv_two_pi), a2);
+}
+
+// Both chains on one lane (host simulation and single-warp use).
+OPVD_HD double batch_symbol_serial(BatchRegs& r, const ToneGates& g1, const ToneGates& g2, bool first_in_call,
+                                   double afc_alpha, const FastMathTable& K) {
+    const double soft = batch_timing(g1.eO, g2.eO, g1.eE, g1.eL, g2.eE, g2.eL, r.timing_freq, r.pos, K);
+    BatchAfc a = {r.freq_offset, r.ph1, r.ph2, r.p1, r.p2};
+    batch_afc(a, g1.O, g1.z40, g1.eO, g2.O, g2.z40, g2.eO, r.t1.inc, r.t2.inc, first_in_call, afc_alpha, K);
+    r.freq_offset = a.freq_offset; r.ph1 = a.ph1; r.ph2 = a.ph2; r.p1 = a.p1; r.p2 = a.p2;
+    if (!first_in_call) batch_lo_fast(r.freq_offset, r.t1, r.t2, K);  // |freq_offset| <= 2 kHz after the clamp
     return soft;
 }
 

@@ -2,26 +2,28 @@
 // (demod_batch_core.cuh).  Used when there are enough streams to fill the machine (thousands):
 // the goal is throughput per issued instruction, not per-symbol latency (kernels_demod_warp.cu).
 //
-// A CTA of 160 threads (5 specialised warps) owns 32 streams; lane = stream in every warp.  Every
-// symbol has two phases separated by CTA barriers:
-//   window phase  helper warps k = 0..3: tone k >> 1, window half k & 1.  30 samples -> three
-//                 10-sample Horner block sums -> three partial gates to shared memory.  There is no
-//                 intra-warp exchange and every instruction does 32 streams' worth of work.
-//                 The post-sum interpolator is linear, so each helper applies it to its own partials.
-//   loop phase    loop warp (warp 4): combines the halves (3 complex FMAs per tone), soft decision, early-late timing loop, AFC (branch-free atan2), LO steps for the
-//                 next symbol, call schedule.  Helper warps 1-3 meanwhile move the next samples from
-//                 HBM into the shared-memory ring.
-// Separate warps keep the loop state out of the helpers' register budget (and vice versa).
-// With one lane per stream in the loop phase the serial arithmetic of the recurrence is amortised
-// over 32 streams (the warp-per-stream kernel spends 330 warp-instructions per stream and symbol,
-// this kernel ~45), and with four threads per stream in the window phase a 16,384-stream bank puts
-// 16 warps on every SM instead of 3.5.
+// A CTA of 128 threads (4 warps) owns 32 streams; lane = stream in every warp, so no instruction ever
+// needs an intra-warp exchange and each one does 32 streams' worth of work.  Every symbol has two
+// phases separated by CTA barriers:
+//   window phase  warp k: tone k >> 1, window half k & 1.  30 samples -> three 10-sample Horner block
+//                 sums -> three partial gates, interpolated (the post-sum interpolator is linear, so
+//                 it is applied per half) -> shared memory.
+//   loop phase    the recurrence, split into its two independent chains:
+//                 warp 0 (tone 1 gates, then the TIMING chain): soft decision, early-late TED, timing
+//                         loop, next position, call schedule, soft-symbol store;
+//                 warp 1 (tone 2 gates, then the AFC chain): phase detector (branch-free atan2), AFC
+//                         loop, previous correlations, LO steps of the next symbol;
+//                 the two exchange ten doubles per stream through shared memory (one named barrier);
+//                 warps 2-3 meanwhile move the next samples from HBM into the shared-memory ring.
+// With one lane per stream the serial arithmetic of the recurrence is amortised over 32 streams (the
+// warp-per-stream kernel spends 330 warp-instructions per stream and symbol, this kernel ~65 in
+// total), and a 16,384-stream bank puts 14 warps on every SM.
 //
 // Sample ring: transposed, ring[row][stream] with row = sample index mod 256, so that lane s always
 // reads bank s whatever its stream's window position is (per-stream rings laid out stream-major
 // give 3-4-way bank conflicts on every load because the window offsets of the 32 streams are
-// unrelated).  Rows 0..63 are mirrored behind row 255: a 61-row window never wraps.  Warps 1-3 fill
-// it with 128-bit global loads (each thread 64 contiguous bytes of its stream per symbol, issued one
+// unrelated).  Rows 0..63 are mirrored behind row 255: a 61-row window never wraps.  Warps 2-3 fill
+// it with 128-bit global loads (each thread 96 contiguous bytes of its stream per symbol, issued one
 // full symbol before they are stored), so HBM is read exactly once, in whole 32-byte sectors.
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -35,51 +37,55 @@ namespace opvd {
 namespace {
 
 constexpr int kSpc = 32;            // streams per CTA
-constexpr int kHelperWarps = 4;     // window-phase roles per stream
-constexpr int kThreads = 32 * (kHelperWarps + 1);  // + the loop warp
+constexpr int kThreads = 128;       // 4 warps
 constexpr int kRingRows = 256;      // samples per stream resident in shared memory (power of two)
 constexpr int kMirrorRows = 64;     // rows 0..63 repeated after row 255
 constexpr int kRows = kRingRows + kMirrorRows;
-constexpr int kStage = 16;          // samples per staging thread and symbol (4 x LDG.128)
-constexpr int kStageAll = 3 * kStage;  // per stream and symbol
+constexpr int kSub = 8;             // samples per 32-byte sector (2 x LDG.128)
+constexpr int kStage = 3 * kSub;    // samples per staging thread and symbol
+constexpr int kStageAll = 2 * kStage;  // per stream and symbol (two staging warps)
 
 struct __align__(16) BatchSmem {
     uint32_t ring[kRows][kSpc];   // 40 KB
-    double2 part[4][3][kSpc];     // [role][E,O,L][stream] partial gates, 6 KB
+    double2 part[4][3][kSpc];     // [warp][E,O,L][stream] interpolated partial gates, 6 KB
     double zq[2][4][kSpc];        // [tone][z.r, z.i, q.r, q.i][stream], 2 KB
+    double xch[10][kSpc];         // loop-phase exchange: 0-6 tone 1 -> AFC warp, 7-9 tone 2 -> timing warp
     double frac[kSpc];            // interpolation fraction f = pos - floor(pos) of the current symbol
     int w0[kSpc];                 // row-relative sample index of window slot 0 of the current symbol
     int live[kSpc];               // stream has a symbol to demodulate
+    int first[kSpc];              // the current symbol is the first of a demodulate() call
     int any_live;
 };
 
-__device__ __forceinline__ void stage_store(BatchSmem& sm, int s, int idx, const uint4 (&v)[4]) {
-    // 16 consecutive samples of stream s starting at sample index idx (multiple of 16)
+// 8 consecutive samples of stream s starting at sample index idx (multiple of 8)
+__device__ __forceinline__ void stage_store8(BatchSmem& sm, int s, int idx, uint4 a, uint4 b) {
     const int row = idx & (kRingRows - 1);
-    const uint32_t w[16] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w,
-                            v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int j = 0; j < 16; ++j) sm.ring[row + j][s] = w[j];
+    for (int j = 0; j < 8; ++j) sm.ring[row + j][s] = w[j];
     if (row < kMirrorRows) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) sm.ring[kRingRows + row + j][s] = w[j];
+        for (int j = 0; j < 8; ++j) sm.ring[kRingRows + row + j][s] = w[j];
     }
 }
-
-// 16 samples of a row starting at idx (multiple of 16); rows are 16-byte aligned and a multiple of 4
+__device__ __forceinline__ void stage_store(BatchSmem& sm, int s, int idx, const uint4 (&v)[6]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) stage_store8(sm, s, idx + kSub * c, v[2 * c], v[2 * c + 1]);
+}
+// 24 samples of a row starting at idx (multiple of 8); rows are 16-byte aligned and a multiple of 4
 // samples long, so only the last chunk of a row can be partial
-__device__ __forceinline__ void stage_load(const uint32_t* row, int idx, int stride, uint4 (&v)[4]) {
+__device__ __forceinline__ void stage_load(const uint32_t* row, int idx, int stride, uint4 (&v)[6]) {
     const uint4* p = reinterpret_cast<const uint4*>(row + idx);
     if (idx + kStage <= stride) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = __ldg(p + j);
+        for (int j = 0; j < 6; ++j) v[j] = __ldg(p + j);
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (idx + 4 * j + 4 <= stride) ? __ldg(p + j) : make_uint4(0u, 0u, 0u, 0u);
+        for (int j = 0; j < 6; ++j) v[j] = (idx + 4 * j + 4 <= stride) ? __ldg(p + j) : make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
-// early-gate correction for the first symbol of a call, both tones (rare: kept out of line)
+// early-gate correction for the first symbol of a call (rare: kept out of line)
 __device__ __noinline__ cplx first_fix_cold(const uint32_t* win, double f, cplx z) {
     return first_symbol_fix_w([&](int kk) { return win[kk * kSpc]; }, f, z);
 }
@@ -92,136 +98,101 @@ __device__ __noinline__ bool schedule_cold(DemodState& st, int mode, long long a
     return live;
 }
 
-__device__ __forceinline__ void publish_lo(BatchSmem& sm, int s, const BatchRegs& r) {
-    sm.zq[0][0][s] = r.t1.z.r; sm.zq[0][1][s] = r.t1.z.i; sm.zq[0][2][s] = r.t1.q.r; sm.zq[0][3][s] = r.t1.q.i;
-    sm.zq[1][0][s] = r.t2.z.r; sm.zq[1][1][s] = r.t2.z.i; sm.zq[1][2][s] = r.t2.q.r; sm.zq[1][3][s] = r.t2.q.i;
+__device__ __forceinline__ void publish_lo(BatchSmem& sm, int s, const ToneLo& t1, const ToneLo& t2) {
+    sm.zq[0][0][s] = t1.z.r; sm.zq[0][1][s] = t1.z.i; sm.zq[0][2][s] = t1.q.r; sm.zq[0][3][s] = t1.q.i;
+    sm.zq[1][0][s] = t2.z.r; sm.zq[1][1][s] = t2.z.i; sm.zq[1][2][s] = t2.q.r; sm.zq[1][3][s] = t2.q.i;
+}
+__device__ __forceinline__ void pair_barrier() {  // warps 0 and 1 only
+    asm volatile("bar.sync 1, 64;" ::: "memory");
 }
 
-// ------------------------------------------------------------------------------------------------
-// loop warp: one lane per stream
-__device__ __forceinline__ void loop_warp(BatchSmem& sm, const StreamBuffers& sb, const SoftBuffers& so,
-                                          DemodState* __restrict__ dstate, int stream, bool valid, int s, int mode,
-                                          int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
+// combine the two halves of one tone (loop phase, warps 0 and 1)
+__device__ __forceinline__ ToneGates finish_tone(BatchSmem& sm, int s, int tone, int w0, bool first) {
+    HalfGates a, b;
+    double2 v;
+    v = sm.part[2 * tone][0][s]; a.E = {v.x, v.y}; v = sm.part[2 * tone][1][s]; a.O = {v.x, v.y};
+    v = sm.part[2 * tone][2][s]; a.L = {v.x, v.y};
+    v = sm.part[2 * tone + 1][0][s]; b.E = {v.x, v.y}; v = sm.part[2 * tone + 1][1][s]; b.O = {v.x, v.y};
+    v = sm.part[2 * tone + 1][2][s]; b.L = {v.x, v.y};
+    ToneLo t;
+    t.z = {sm.zq[tone][0][s], sm.zq[tone][1][s]};
+    t.q = {sm.zq[tone][2][s], sm.zq[tone][3][s]};
+    t.inc = 0.0;
+    cplx fix = {0.0, 0.0};
+    if (first)  // early-gate clamp (:237), once per call; window n is still in the ring
+        fix = first_fix_cold(&sm.ring[w0 & (kRingRows - 1)][s], sm.frac[s], t.z);
+    return batch_finish_tone(a, b, t, fix);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 4)
+demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
+                   int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BatchSmem& sm = *reinterpret_cast<BatchSmem*>(smem_raw);
+    const int s = threadIdx.x & 31, k = threadIdx.x >> 5;
+    const int stream_raw = blockIdx.x * kSpc + s;
+    const bool valid = stream_raw < n_streams;
+    const int stream = valid ? stream_raw : n_streams - 1;
     const long long row0 = sb.row_base;
-    DemodState st = dstate[stream];
-    const long long avail = sb.avail[stream];
-    double* const soft_row = so.soft + (long long)stream * so.stride - so.base;
-    BatchRegs r;
-    r.freq_offset = st.freq_offset; r.ph1 = st.ph1; r.ph2 = st.ph2; r.pos = st.pos; r.timing_freq = st.timing_freq;
-    r.p1 = st.p1; r.p2 = st.p2;
-    batch_lo(r.freq_offset, r.t1, r.t2);  // general version: a -o offset may exceed the fast range
-    const long long n_sym0 = st.n_sym, origin0 = st.origin;
-    bool live = valid && schedule_cold(st, mode, avail, final_flag != 0);
-    r.pos = st.pos;
-    double call_len_d = (double)st.call_len, f = 0.0;
-    int origin_rel = (int)(st.origin - row0);
-    int w0 = 0;
-    // st lives in local memory (its address goes to the out-of-line scheduler): keep the per-symbol
-    // counters in registers and write them back only around that call
-    int sym_in_call = st.sym_in_call;
-    double* soft_ptr = soft_row + st.n_sym;
-    if (live) {
-        const int b = __double2int_rz(r.pos);  // pos >= 0: truncation == floor (:125)
-        f = r.pos - (double)b;
-        w0 = origin_rel + b - kWinLead;
-    }
-    sm.w0[s] = w0;
-    sm.frac[s] = f;
-    sm.live[s] = live ? 1 : 0;
-    publish_lo(sm, s, r);
-    {
-        const int any = __any_sync(0xffffffffu, live);
-        if (s == 0) sm.any_live = any;
-    }
-    __syncthreads();  // state of symbol 0 published
-    __syncthreads();  // ring primed by the helpers
+    const uint32_t* __restrict__ row = sb.iq + (long long)stream * sb.stride;  // row[r] = absolute sample row0 + r
+    const int stride_i = (int)sb.stride;
 
-    while (sm.any_live) {
-        const bool first = sym_in_call == 0;
-        __syncthreads();  // partial gates ready
+    // ---- loop-phase state.  warp 0: timing chain + call schedule; warp 1: AFC chain
+    DemodState st;                      // warp 0 (lives in local memory: only the scheduler touches it)
+    double pos = 0.0, timing_freq = 0.0, call_len_d = 0.0;  // warp 0
+    long long avail = 0, n_sym0 = 0, origin0 = 0;           // warp 0
+    int origin_rel = 0, sym_in_call = 0;                    // warp 0
+    double* soft_row = nullptr;
+    double* soft_ptr = nullptr;                             // warp 0
+    BatchAfc afc = {0.0, 0.0, 0.0, {0.0, 0.0}, {0.0, 0.0}};  // warp 1
+    double inc1 = 0.0, inc2 = 0.0;                          // warp 1: LO phase steps of the current symbol
+    if (k == 0) {
+        st = dstate[stream];
+        avail = sb.avail[stream];
+        soft_row = so.soft + (long long)stream * so.stride - so.base;
+        soft_ptr = soft_row + st.n_sym;
+        n_sym0 = st.n_sym; origin0 = st.origin;
+        timing_freq = st.timing_freq;
+        const bool live = valid && schedule_cold(st, mode, avail, final_flag != 0);
+        pos = st.pos;
+        sym_in_call = st.sym_in_call;
+        call_len_d = (double)st.call_len;
+        origin_rel = (int)(st.origin - row0);
+        int w0 = 0;
+        double f = 0.0;
         if (live) {
-            // one tone at a time (the barrier keeps the second tone's loads from being hoisted, which
-            // would double the live registers)
-            const uint32_t* win = &sm.ring[w0 & (kRingRows - 1)][s];  // window n is still in the ring
-            ToneGates g1, g2;
-            {
-                HalfGates a, b;
-                double2 v;
-                v = sm.part[0][0][s]; a.E = {v.x, v.y}; v = sm.part[0][1][s]; a.O = {v.x, v.y}; v = sm.part[0][2][s]; a.L = {v.x, v.y};
-                v = sm.part[1][0][s]; b.E = {v.x, v.y}; v = sm.part[1][1][s]; b.O = {v.x, v.y}; v = sm.part[1][2][s]; b.L = {v.x, v.y};
-                cplx fix = {0.0, 0.0};
-                if (first) fix = first_fix_cold(win, f, r.t1.z);  // early-gate clamp (:237), once per call
-                g1 = batch_finish_tone(a, b, r.t1, fix);
-            }
-            asm volatile("" ::: "memory");
-            {
-                HalfGates a, b;
-                double2 v;
-                v = sm.part[2][0][s]; a.E = {v.x, v.y}; v = sm.part[2][1][s]; a.O = {v.x, v.y}; v = sm.part[2][2][s]; a.L = {v.x, v.y};
-                v = sm.part[3][0][s]; b.E = {v.x, v.y}; v = sm.part[3][1][s]; b.O = {v.x, v.y}; v = sm.part[3][2][s]; b.L = {v.x, v.y};
-                cplx fix = {0.0, 0.0};
-                if (first) fix = first_fix_cold(win, f, r.t2.z);
-                g2 = batch_finish_tone(a, b, r.t2, fix);
-            }
-            const double soft = batch_symbol_serial(r, g1, g2, first, afc_alpha, g_fm);
-            *soft_ptr++ = soft;
-            sym_in_call = 1;  // any non-zero value: the open call has produced symbols
-            // ---- next symbol of this stream
-            if (!((r.pos + 40.0) + 10.0 < call_len_d)) {  // :221 fails: close the call, maybe open the next
-                st.n_sym = (long long)(soft_ptr - soft_row);
-                st.sym_in_call = sym_in_call;
-                st.pos = r.pos;
-                live = schedule_cold(st, mode, avail, final_flag != 0);
-                r.pos = st.pos;
-                sym_in_call = st.sym_in_call;
-                call_len_d = (double)st.call_len;
-                origin_rel = (int)(st.origin - row0);
-            }
-            if (live) {
-                const int b2 = __double2int_rz(r.pos);
-                f = r.pos - (double)b2;
-                w0 = origin_rel + b2 - kWinLead;
-                sm.w0[s] = w0;
-                sm.frac[s] = f;
-                publish_lo(sm, s, r);
-            } else {
-                sm.live[s] = 0;
-            }
+            const int b = __double2int_rz(pos);  // pos >= 0: truncation == floor (:125)
+            f = pos - (double)b;
+            w0 = origin_rel + b - kWinLead;
         }
+        sm.w0[s] = w0;
+        sm.frac[s] = f;
+        sm.live[s] = live ? 1 : 0;
+        sm.first[s] = sym_in_call == 0;
         const int any = __any_sync(0xffffffffu, live);
         if (s == 0) sm.any_live = any;
-        __syncthreads();  // state of the next symbol published, ring advanced
+    } else if (k == 1) {
+        const DemodState* d = dstate + stream;
+        afc.freq_offset = d->freq_offset; afc.ph1 = d->ph1; afc.ph2 = d->ph2; afc.p1 = d->p1; afc.p2 = d->p2;
+        ToneLo t1, t2;
+        batch_lo(afc.freq_offset, t1, t2);  // general version: a -o offset may exceed the fast range
+        inc1 = t1.inc; inc2 = t2.inc;
+        publish_lo(sm, s, t1, t2);
     }
-
-    // ---- persist the stream's state
-    if (valid) {
-        st.n_sym = (long long)(soft_ptr - soft_row);
-        st.sym_in_call = sym_in_call;
-        st.freq_offset = r.freq_offset; st.ph1 = r.ph1; st.ph2 = r.ph2; st.pos = r.pos; st.timing_freq = r.timing_freq;
-        st.p1 = r.p1; st.p2 = r.p2;
-        dstate[stream] = st;
-        unsigned long long dsym = (unsigned long long)(st.n_sym - n_sym0);
-        unsigned long long dsmp = (unsigned long long)(st.origin - origin0);
-        if (st.flags & kFlagDone) dsmp = (unsigned long long)(avail - origin0);
-        if (dsym) atomicAdd(&counters[kCtrSymbols], dsym);
-        if (dsmp) atomicAdd(&counters[kCtrSamples], dsmp);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// helper warps: window phase (all four) and ring staging (warps 1-3)
-__device__ __forceinline__ void helper_warp(BatchSmem& sm, const uint32_t* __restrict__ row, int stride_i, int s, int k) {
     __syncthreads();  // state of symbol 0 published
-    // ---- prime the ring: everything up to w0 + 208.. of each live stream
-    int fill;  // samples [.., fill) of this thread's stream have been requested (multiple of 16)
-    {
+
+    // ---- prime the ring (warps 2-3): everything up to w0 + 208.. of each live stream
+    int fill = 0;  // samples [.., fill) of this thread's stream have been requested (multiple of 8)
+    if (k >= 2) {
         const int w0 = sm.w0[s];
-        fill = (w0 < 0 ? 0 : w0) & ~(kStage - 1);
-        if (k >= 1 && sm.live[s]) {
+        fill = (w0 < 0 ? 0 : w0) & ~(kSub - 1);
+        if (sm.live[s]) {
             while (fill + kStageAll <= w0 + kRingRows) {
-                const int idx = fill + kStage * (k - 1);
+                const int idx = fill + kStage * (k - 2);
                 if (idx < stride_i) {
-                    uint4 v[4];
+                    uint4 v[6];
                     stage_load(row, idx, stride_i, v);
                     stage_store(sm, s, idx, v);
                 }
@@ -231,13 +202,14 @@ __device__ __forceinline__ void helper_warp(BatchSmem& sm, const uint32_t* __res
     }
     __syncthreads();  // ring primed
 
-    uint4 pend[4];  // 16 samples requested during the previous symbol, stored during this one
+    uint4 pend[6];  // warps 2-3: 24 samples requested during the previous symbol, stored during this one
     int pend_idx = -1;
     const int tone = k >> 1, half = k & 1;
+
     while (sm.any_live) {
         const int lv = sm.live[s];
         const int w0 = sm.w0[s];
-        // ---- window phase
+        // ---- window phase (all four warps)
         if (lv) {
             const uint32_t* src = &sm.ring[(w0 & (kRingRows - 1)) + 30 * half][s];
             double I[31], Q[31];  // slots 30h .. 30h+29, and slot 60 for the late gate's edge term (h = 1)
@@ -252,13 +224,70 @@ __device__ __forceinline__ void helper_warp(BatchSmem& sm, const uint32_t* __res
             sm.part[k][2][s] = make_double2(g.L.r, g.L.i);
         }
         __syncthreads();  // partial gates ready
-        // ---- staging (warps 1-3): store the 16 samples requested one symbol ago (their rows hold samples
-        // older than any live window), then request the next ones; the loads have a whole symbol to land
-        if (k >= 1) {
+        const bool first = sm.first[s] != 0;
+        if (k == 0) {
+            // ---- tone 1 gates, then the timing chain
+            bool live = lv != 0;
+            ToneGates g1;
+            if (live) {
+                g1 = finish_tone(sm, s, 0, w0, first);
+                sm.xch[0][s] = g1.eE; sm.xch[1][s] = g1.eO; sm.xch[2][s] = g1.eL;
+                sm.xch[3][s] = g1.O.r; sm.xch[4][s] = g1.O.i; sm.xch[5][s] = g1.z40.r; sm.xch[6][s] = g1.z40.i;
+            }
+            pair_barrier();
+            if (live) {
+                const double eE2 = sm.xch[7][s], eO2 = sm.xch[8][s], eL2 = sm.xch[9][s];
+                const double soft = batch_timing(g1.eO, eO2, g1.eE, g1.eL, eE2, eL2, timing_freq, pos, g_fm);
+                *soft_ptr++ = soft;
+                sym_in_call = 1;  // any non-zero value: the open call has produced symbols
+                // ---- next symbol of this stream
+                if (!((pos + 40.0) + 10.0 < call_len_d)) {  // :221 fails: close the call, maybe open the next
+                    st.n_sym = (long long)(soft_ptr - soft_row);
+                    st.sym_in_call = sym_in_call;
+                    st.pos = pos;
+                    live = schedule_cold(st, mode, avail, final_flag != 0);
+                    pos = st.pos;
+                    sym_in_call = st.sym_in_call;
+                    call_len_d = (double)st.call_len;
+                    origin_rel = (int)(st.origin - row0);
+                }
+                if (live) {
+                    const int b2 = __double2int_rz(pos);
+                    sm.w0[s] = origin_rel + b2 - kWinLead;
+                    sm.frac[s] = pos - (double)b2;
+                    sm.first[s] = sym_in_call == 0;
+                } else {
+                    sm.live[s] = 0;
+                }
+            }
+            const int any = __any_sync(0xffffffffu, live);
+            if (s == 0) sm.any_live = any;
+        } else if (k == 1) {
+            // ---- tone 2 gates, then the AFC chain and the LO steps of the next symbol
+            ToneGates g2;
+            if (lv) {
+                g2 = finish_tone(sm, s, 1, w0, first);
+                sm.xch[7][s] = g2.eE; sm.xch[8][s] = g2.eO; sm.xch[9][s] = g2.eL;
+            }
+            pair_barrier();
+            if (lv) {
+                const double eO1 = sm.xch[1][s];
+                const cplx O1 = {sm.xch[3][s], sm.xch[4][s]}, z40_1 = {sm.xch[5][s], sm.xch[6][s]};
+                batch_afc(afc, O1, z40_1, eO1, g2.O, g2.z40, g2.eO, inc1, inc2, first, afc_alpha, g_fm);
+                if (!first) {
+                    ToneLo t1, t2;
+                    batch_lo_fast(afc.freq_offset, t1, t2, g_fm);  // |freq_offset| <= 2 kHz after the AFC clamp
+                    inc1 = t1.inc; inc2 = t2.inc;
+                    publish_lo(sm, s, t1, t2);
+                }
+            }
+        } else {
+            // ---- staging (warps 2-3): store the 24 samples requested one symbol ago (their rows hold samples
+            // older than any live window), then request the next ones; the loads have a whole symbol to land
             if (pend_idx >= 0) stage_store(sm, s, pend_idx, pend);
             pend_idx = -1;
             if (lv && fill + kStageAll <= w0 + kRingRows) {
-                const int idx = fill + kStage * (k - 1);
+                const int idx = fill + kStage * (k - 2);
                 if (idx < stride_i) {
                     stage_load(row, idx, stride_i, pend);
                     pend_idx = idx;
@@ -268,23 +297,23 @@ __device__ __forceinline__ void helper_warp(BatchSmem& sm, const uint32_t* __res
         }
         __syncthreads();  // state of the next symbol published, ring advanced
     }
-}
 
-}  // namespace
-
-__global__ void __launch_bounds__(kThreads, 4)
-demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
-                   int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    BatchSmem& sm = *reinterpret_cast<BatchSmem*>(smem_raw);
-    const int s = threadIdx.x & 31, k = threadIdx.x >> 5;
-    const int stream_raw = blockIdx.x * kSpc + s;
-    const bool valid = stream_raw < n_streams;
-    const int stream = valid ? stream_raw : n_streams - 1;
-    if (k == kHelperWarps) {
-        loop_warp(sm, sb, so, dstate, stream, valid, s, mode, final_flag, afc_alpha, counters);
-    } else {
-        helper_warp(sm, sb.iq + (long long)stream * sb.stride, (int)sb.stride, s, k);
+    // ---- persist the streams' state: warp 0 writes the record, warp 1 then patches the AFC fields
+    if (k == 0 && valid) {
+        st.n_sym = (long long)(soft_ptr - soft_row);
+        st.sym_in_call = sym_in_call;
+        st.pos = pos; st.timing_freq = timing_freq;
+        dstate[stream] = st;
+        unsigned long long dsym = (unsigned long long)(st.n_sym - n_sym0);
+        unsigned long long dsmp = (unsigned long long)(st.origin - origin0);
+        if (st.flags & kFlagDone) dsmp = (unsigned long long)(avail - origin0);
+        if (dsym) atomicAdd(&counters[kCtrSymbols], dsym);
+        if (dsmp) atomicAdd(&counters[kCtrSamples], dsmp);
+    }
+    __syncthreads();
+    if (k == 1 && valid) {
+        DemodState* d = dstate + stream;
+        d->freq_offset = afc.freq_offset; d->ph1 = afc.ph1; d->ph2 = afc.ph2; d->p1 = afc.p1; d->p2 = afc.p2;
     }
 }
 
