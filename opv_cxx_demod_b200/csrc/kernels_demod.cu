@@ -305,16 +305,14 @@ static cudaError_t launch_t(const StreamBuffers& sb, const SoftBuffers& so, Demo
 }
 
 int demod_auto_lanes(int n_streams) {
-    // aim for >= ~12 resident warps per SM (3 per scheduler) on 148 SMs; more lanes per stream cost
-    // redundant loop arithmetic, so take the smallest split that fills the machine
+    // Small banks are bound by the per-symbol latency of the serial recurrence: one warp per stream, as
+    // long as every stream's warp is resident at once (12 warps per SM at the kernel's register count).
+    // Larger banks: the batched kernel (32 streams per CTA), which spends ~5x fewer instructions per
+    // stream and symbol.  The lane kernels (1, 2, 4) stay selectable for comparison.
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // small banks are bound by the per-symbol latency of the serial recurrence: one warp per stream
-    if ((long long)n_streams <= 28ll * sms) return 32;
-    const long long want_warps = 12ll * sms;
-    if ((long long)n_streams / 32 >= want_warps) return 1;
-    if ((long long)n_streams / 16 >= want_warps) return 2;
-    return 4;
+    if ((long long)n_streams <= 12ll * sms) return 32;
+    return 64;
 }
 
 cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,

@@ -57,10 +57,23 @@ struct __align__(16) BatchSmem {
     int any_live;
 };
 
+constexpr uint32_t kQBias = 0x80000000u;
+// ring word (I raw, Q offset-binary) -> doubles.  I through I2F.F64.S16 (XU pipe), Q through the 2^52
+// bias trick (integer pipe + one DADD): the window phase converts 60 components per thread and symbol
+// and would otherwise be bound by the XU pipe (8 cycles per warp instruction).
+__device__ __forceinline__ void unpack_ring(uint32_t w, double& I, double& Q) {
+    I = (double)(int16_t)(w & 0xFFFFu);
+    Q = __hiloint2double(0x43300000, (int)(w >> 16)) - 4503599627403264.0;  // 2^52 + 2^15
+}
+__device__ __forceinline__ uint32_t ring_raw(uint32_t w) { return w ^ kQBias; }
+
 // 8 consecutive samples of stream s starting at sample index idx (multiple of 8)
 __device__ __forceinline__ void stage_store8(BatchSmem& sm, int s, int idx, uint4 a, uint4 b) {
     const int row = idx & (kRingRows - 1);
-    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    // the ring holds Q with its sign bit flipped (offset binary): unpack_ring() then builds the double
+    // 2^52 + (Q + 32768) without a per-use XOR
+    const uint32_t w[8] = {a.x ^ kQBias, a.y ^ kQBias, a.z ^ kQBias, a.w ^ kQBias,
+                           b.x ^ kQBias, b.y ^ kQBias, b.z ^ kQBias, b.w ^ kQBias};
 #pragma unroll
     for (int j = 0; j < 8; ++j) sm.ring[row + j][s] = w[j];
     if (row < kMirrorRows) {
@@ -87,7 +100,7 @@ __device__ __forceinline__ void stage_load(const uint32_t* row, int idx, int str
 
 // early-gate correction for the first symbol of a call (rare: kept out of line)
 __device__ __noinline__ cplx first_fix_cold(const uint32_t* win, double f, cplx z) {
-    return first_symbol_fix_w([&](int kk) { return win[kk * kSpc]; }, f, z);
+    return first_symbol_fix_w([&](int kk) { return ring_raw(win[kk * kSpc]); }, f, z);
 }
 // call scheduling out of line.  Everything it touches by reference lives in local memory, so the
 // hot loop hands it copies: the position comes back through st.pos.
@@ -131,7 +144,9 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
                    int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BatchSmem& sm = *reinterpret_cast<BatchSmem*>(smem_raw);
-    const int s = threadIdx.x & 31, k = threadIdx.x >> 5;
+    // roles rotate with the CTA index: warps land on SM sub-partitions by warp id, and the loop-phase
+    // chains (roles 0 and 1) are heavier than the staging roles, so co-resident CTAs spread them out
+    const int s = threadIdx.x & 31, k = ((threadIdx.x >> 5) + blockIdx.x) & 3;
     const int stream_raw = blockIdx.x * kSpc + s;
     const bool valid = stream_raw < n_streams;
     const int stream = valid ? stream_raw : n_streams - 1;
@@ -214,9 +229,9 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
             const uint32_t* src = &sm.ring[(w0 & (kRingRows - 1)) + 30 * half][s];
             double I[31], Q[31];  // slots 30h .. 30h+29, and slot 60 for the late gate's edge term (h = 1)
 #pragma unroll
-            for (int j = 0; j < 30; ++j) unpack_iq_mixed(src[j * kSpc], I[j], Q[j]);
+            for (int j = 0; j < 30; ++j) unpack_ring(src[j * kSpc], I[j], Q[j]);
             I[30] = 0.0; Q[30] = 0.0;
-            if (half) unpack_iq(src[30 * kSpc], I[30], Q[30]);
+            if (half) unpack_ring(src[30 * kSpc], I[30], Q[30]);
             const cplx z = {sm.zq[tone][0][s], sm.zq[tone][1][s]}, q = {sm.zq[tone][2][s], sm.zq[tone][3][s]};
             const HalfGates g = batch_half_gates(I, Q, z, q, sm.frac[s], half);
             sm.part[k][0][s] = make_double2(g.E.r, g.E.i);
