@@ -6,8 +6,10 @@ the HBM roofline of the front-end kernel, with the reference's CPU opv-demod tim
 
 Workload at N=1 = BASELINE.json configs[1]: 1,024 streams x 10 s (250 frames, 21.68 M samples,
 86.7 MB each; 88.8 GB resident) of synthetic opv-mod-like captures with AWGN, Eb/N0 swept
-2..10 dB across streams.  N>1: every rank owns its own 1,024 streams ("scaling": "weak"; the
-16,384-stream bank of configs[4] is `--streams 16384 --seconds 1`).  A step = one pass of the
+2..10 dB across streams.  N>1: every rank owns its own 1,024 streams ("scaling": "weak").  The
+north-star target configuration (over 16,384 concurrent streams, BASELINE configs[4]) is measured in
+the same run as the `channel_bank` object: 18,944 streams per GPU (4 CTAs x 32 streams on each of the
+148 SMs) x 14 frames, resident in HBM, same chain, same timing rules.  A step = one pass of the
 whole chain (estimate -> demod -> sync tracker -> Viterbi) over the rank's bank in streaming mode
 (`opv-demod -s` semantics), from fresh per-stream state.
 
@@ -45,6 +47,10 @@ def parse_args():
     ap.add_argument("--seconds", type=float, default=10.0, help="capture length per stream")
     ap.add_argument("--lanes", type=int, default=0, help="GPU lanes per stream (0 = automatic)")
     ap.add_argument("--e2e-seconds", type=float, default=0.52, help="capture length per stream for the e2e leg")
+    ap.add_argument("--bank-streams", type=int, default=0,
+                    help="streams per GPU of the channel-bank leg (0 = 4 CTAs x 32 streams per SM, 18,944 on a B200)")
+    ap.add_argument("--bank-frames", type=int, default=14, help="frames per stream of the channel-bank leg")
+    ap.add_argument("--no-bank", action="store_true", help="skip the >=16,384-stream channel-bank leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -193,6 +199,73 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def run_channel_bank(args, pkg, torch, dev, local_rank, rank, world, barrier, reduce_max_ms, reduce_counters, peak, mb):
+    """BASELINE configs[4] / north-star target: a bank of over 16,384 concurrent streams per GPU, resident in
+    HBM (distinct memory per stream), demodulated from fresh state.  Per-GPU work is fixed (weak scaling)."""
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    S = args.bank_streams or 4 * 32 * sms          # 4 resident CTAs x 32 streams on every SM: 18,944 on a B200
+    n_frames = args.bank_frames
+    max_lead = 4000
+    n = n_frames * FRAME_SAMPLES + max_lead + 4000
+    stride = (n + 63) // 64 * 64
+    buf = torch.empty((S, stride), dtype=torch.int32, device=dev)
+    sp = pkg.make_synth(S, n_frames, stride, n, seed=20261018, ebn0_lo_db=2.0, ebn0_hi_db=10.0, max_lead=max_lead,
+                        first_stream=rank * S)
+    pkg.synth_bank(buf.data_ptr(), sp, device=local_rank)
+    bank = pkg.DemodBank(S, streaming=True, device=local_rank, lanes_per_stream=args.lanes)
+    bank.attach_device_iq(buf.data_ptr(), stride, n, keepalive=buf)
+    steps, warm = max(2, min(args.steps, 3)), 3
+    per = {"estimate": 0.0, "demod": 0.0, "track": 0.0, "decode": 0.0, "total": 0.0}
+    for _ in range(warm):
+        bank.reset()
+        bank.run(final=True, sync=True)
+    barrier()
+    for _ in range(steps):
+        bank.reset()
+        bank.run(final=True, sync=True)
+        ms = bank.last_run_ms()
+        for k in per:
+            per[k] += ms[k]
+    barrier()
+    c = bank.counters()
+    bank.bert_check(sp)
+    ber = bank.counters()
+    dev_ms = reduce_max_ms(per["total"], dev)
+    demod_ms_max = reduce_max_ms(per["demod"], dev)
+    tot = reduce_counters({k: c[k] for k in ("samples", "frames_decoded", "acs")}
+                          | {"bit_errors": ber["bit_errors"], "frames_compared": ber["frames_compared"]}, dev)
+    value = tot["samples"] * steps / (dev_ms * 1e-3) / 1e6
+    demod_ms = per["demod"] / steps
+    ach = c["samples"] * 4 / (demod_ms * 1e-3) / 1e9
+    out = {
+        "workload": f"{S} streams x {n_frames} frames per GPU ({S * n * 4 / 1e9:.1f} GB resident, distinct memory per "
+                    f"stream), AWGN Eb/N0 2-10 dB, stream mode, fresh state every step",
+        "streams_per_gpu": S, "streams_total": S * world, "frames_per_stream": n_frames, "steps": steps, "warmup": warm,
+        "value": round(value, 2), "unit": UNIT, "frames_per_s": round(tot["frames_decoded"] * steps / (dev_ms * 1e-3), 1),
+        "ms_per_step": round(dev_ms / steps, 3),
+        "kernel_ms_per_step": {k: round(v / steps, 3) for k, v in per.items()},
+        "demod_only_msps": round(tot["samples"] * steps / (demod_ms_max * 1e-3) / 1e6, 2),
+        "ber": (tot["bit_errors"] / (tot["frames_compared"] * 1072.0)) if tot["frames_compared"] else None,
+        "roofline": {"bound": "hbm", "kernel": bank.demod_variant(), "achieved": round(ach, 2), "peak": peak,
+                     "unit": "GB/s", "frac": round(ach / peak, 5), "launch_ms": round(demod_ms, 3),
+                     "algorithmic_bytes_per_launch": int(c["samples"] * 4)},
+        "note": "the estimate kernel is a fixed cost per stream (first 40,000 samples); with 14-frame captures it is a "
+                "visible share of the step, with 10-s captures it is 0.4 %",
+    }
+    if mb:
+        dfma = c["samples"] * 12.0 / (demod_ms * 1e-3)
+        out["roofline"]["fp64"] = {"achieved_dfma_per_s": round(dfma, 1), "peak_dfma_per_s": mb["dfma_per_s"],
+                                   "frac": round(dfma / mb["dfma_per_s"], 4),
+                                   "note": "12 DFMA per sample is the Horner correlator's algorithmic minimum "
+                                           "(60-sample window x 2 tones x 4 per 40 new samples); conversions, gate "
+                                           "combination and the loop arithmetic come on top"}
+    bank.close()
+    del buf
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -271,11 +344,15 @@ def main():
     ach = counters["samples"] * 4 / (demod_ms * 1e-3) / 1e9
     traffic = load_profile_json("roofline_traffic.json")
     mb = load_profile_json("microbench_r01.json")
+    variant = bank.demod_variant()
     roofline = {"bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
-                "traffic": (traffic or {}).get("demod_kernel_dram_bytes_per_sample"),
-                "kernel": "demod_kernel", "launch_ms": round(demod_ms, 3), "peak_source": peak_src,
-                "note": "FP64-pipe bound (reference arithmetic is FP64); see fp64"}
-    fp64_ops_per_sample = 24.0  # FP64 instructions per sample of the restructured correlator
+                "traffic": (traffic or {}).get(variant + "_dram_bytes_per_launch_per_algorithmic_byte"),
+                "kernel": variant, "launch_ms": round(demod_ms, 3), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(counters["samples"] * 4),
+                "note": "1,024 streams are bound by the per-symbol latency of the serial timing/AFC recurrence "
+                        "(one warp per stream, 6.9 warps per SM), not by HBM or a pipe; the HBM/FP64-bound regime "
+                        "is the channel_bank object (DESIGN.md section 3)"}
+    fp64_ops_per_sample = 12.0  # DFMAs per sample of the Horner correlator (60-sample window, 2 tones, 4 per step)
     if mb:
         roofline["fp64"] = {"achieved_dfma_per_s": round(counters["samples"] * fp64_ops_per_sample / (demod_ms * 1e-3), 1),
                             "peak_dfma_per_s": mb["dfma_per_s"],
@@ -344,6 +421,16 @@ def main():
             mism += int((ref[:m] != got[:m]).any(axis=1).sum()) if got.shape[0] >= m else m
         spot = {"streams": cores, "frames_compared": compared, "frame_mismatches": mism}
 
+    # ---- channel bank (north-star target: over 16,384 concurrent streams): same chain, same timing rules
+    channel_bank = None
+    if not args.no_bank:
+        bank.close()
+        del bank_buf
+        torch.cuda.empty_cache()
+        channel_bank = run_channel_bank(args, pkg, torch, dev, local_rank, rank, world, barrier, reduce_max_ms,
+                                        reduce_counters, peak, mb)
+        bank = None
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -359,10 +446,12 @@ def main():
             "counters": tot,
             "ber": (tot["bit_errors"] / (tot["frames_compared"] * 1072.0)) if tot["frames_compared"] else None,
             "roofline": roofline, "viterbi": viterbi, "cpu_baseline": cpu_baseline, "parity_spotcheck": spot,
-            "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks,
+            "channel_bank": channel_bank,
+            "e2e": e2e, "gpu_launches": 5 * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    bank.close()
+    if bank is not None:
+        bank.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

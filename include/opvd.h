@@ -52,7 +52,9 @@ typedef struct opvd_config {
                                   opvd_push_iq*; 0 when captures are attached with opvd_attach_device_iq */
     int64_t max_symbols;       /* soft-symbol buffer capacity per stream; 0 = derived from max_samples */
     int32_t max_frames;        /* per-stream frame ring (frames decoded but not yet polled); 0 = derived */
-    int32_t lanes_per_stream;  /* GPU lanes cooperating on one stream; 0 = automatic */
+    int32_t lanes_per_stream;  /* demodulator kernel variant: 0 = chosen from n_streams; 1, 2, 4 = lanes per stream
+                                  of the lane kernels; 32 = one warp per stream (small banks, lowest per-symbol
+                                  latency); 64 = batched, 32 streams per 128-thread CTA (large banks) */
 } opvd_config;
 
 typedef struct opvd_event {
@@ -135,6 +137,8 @@ int opvd_counters_device_ptr(opvd_handle* h, void** out);
 /* elapsed GPU time of the last opvd_run, measured with CUDA events on the handle's stream:
  * ms[0]=estimate, ms[1]=demod, ms[2]=track, ms[3]=decode, ms[4]=total */
 int opvd_last_run_ms(opvd_handle* h, float* ms5);
+/* the demodulator kernel variant in use (opvd_config.lanes_per_stream with 0 resolved) */
+int opvd_demod_lanes(opvd_handle* h);
 
 /* ---- stage-level seams (parity tests) */
 /* FrameDecoder::decode (:854-898): n payloads of 2144 doubles -> n frames of 134 bytes + metrics (-1 = dropped) */

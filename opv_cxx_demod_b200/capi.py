@@ -29,7 +29,7 @@ COUNTER_NAMES = ["samples", "symbols", "frames_ready", "frames_decoded", "frames
 EXPORTS = ["opvd_create", "opvd_destroy", "opvd_reset", "opvd_strerror", "opvd_last_cuda_error", "opvd_version",
            "opvd_push_iq", "opvd_push_iq_all", "opvd_attach_device_iq", "opvd_run", "opvd_sync",
            "opvd_poll_frames", "opvd_poll_events", "opvd_get_soft", "opvd_get_stream_info",
-           "opvd_get_counters", "opvd_counters_device_ptr", "opvd_last_run_ms", "opvd_stage_decode",
+           "opvd_get_counters", "opvd_counters_device_ptr", "opvd_last_run_ms", "opvd_demod_lanes", "opvd_stage_decode",
            "opvd_stage_decode_dev", "opvd_synth_bank", "opvd_bert_check"]
 
 
@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
     L.opvd_get_counters.argtypes = [H, C.c_void_p, C.c_int32]
     L.opvd_counters_device_ptr.argtypes = [H, C.POINTER(C.c_void_p)]
     L.opvd_last_run_ms.argtypes = [H, C.c_void_p]
+    L.opvd_demod_lanes.argtypes = [H]
     L.opvd_stage_decode.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.opvd_stage_decode_dev.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.opvd_synth_bank.argtypes = [C.c_int32, C.POINTER(Synth), C.c_void_p]

@@ -421,6 +421,12 @@ int opvd_sync(opvd_handle* h) {
     return OPVD_OK;
 }
 
+int opvd_demod_lanes(opvd_handle* h) {
+    if (!h) return OPVD_ERR_ARG;
+    CK(cudaSetDevice(h->dev));
+    return h->cfg.lanes_per_stream > 0 ? h->cfg.lanes_per_stream : demod_auto_lanes(h->S);
+}
+
 int opvd_last_run_ms(opvd_handle* h, float* ms5) {
     if (!h || !ms5) return OPVD_ERR_ARG;
     if (!h->have_times) return OPVD_ERR_STATE;

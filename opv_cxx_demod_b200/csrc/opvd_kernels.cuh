@@ -57,6 +57,9 @@ cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodSt
                          int mode, int final_flag, double afc_alpha, int lanes_per_stream,
                          unsigned long long* counters, cudaStream_t st);
 
+// the lanes_per_stream value launch_demod resolves 0 (automatic) to
+int demod_auto_lanes(int n_streams);
+
 // warp-per-stream variant (kernels_demod_warp.cu); selected by launch_demod for lanes_per_stream == 32
 cudaError_t launch_demod_warp(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,

@@ -54,6 +54,7 @@ class DemodBank:
         if getattr(self, "_h", None):
             self._lib.opvd_destroy(self._h)
             self._h = None
+        self._keepalive = None
 
     def __del__(self):
         try:
@@ -124,6 +125,11 @@ class DemodBank:
         ms = (C.c_float * 5)()
         self._ck(self._lib.opvd_last_run_ms(self._h, ms), "opvd_last_run_ms")
         return dict(zip(("estimate", "demod", "track", "decode", "total"), [float(x) for x in ms]))
+
+    def demod_variant(self) -> str:
+        """Name of the demodulator kernel this bank runs (automatic selection resolved)."""
+        lanes = int(self._lib.opvd_demod_lanes(self._h))
+        return {32: "demod_warp_kernel", 64: "demod_batch_kernel"}.get(lanes, f"demod_kernel_t(lanes={lanes})")
 
     # -- output --------------------------------------------------------------------------------
     def poll_frames(self, max_frames: int | None = None) -> Frames:
