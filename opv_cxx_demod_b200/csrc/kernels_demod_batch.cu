@@ -9,11 +9,11 @@
 //                 sums -> three partial gates, interpolated (the post-sum interpolator is linear, so
 //                 it is applied per half) -> shared memory.
 //   loop phase    the recurrence, split into its two independent chains:
-//                 warp 0 (tone 1 gates, then the TIMING chain): soft decision, early-late TED, timing
-//                         loop, next position, call schedule, soft-symbol store;
-//                 warp 1 (tone 2 gates, then the AFC chain): phase detector (branch-free atan2), AFC
-//                         loop, previous correlations, LO steps of the next symbol;
-//                 the two exchange ten doubles per stream through shared memory (one named barrier);
+//                 warp 0 (TIMING chain): gate energies, soft decision, early-late TED, timing loop,
+//                         next position, call schedule, soft-symbol store;
+//                 warp 1 (AFC chain): on-time sums, phase detector (branch-free atan2), AFC loop,
+//                         previous correlations, LO steps of the next symbol;
+//                 each combines the helpers' partial gates it needs itself (cheaper than an exchange);
 //                 warps 2-3 meanwhile move the next samples from HBM into the shared-memory ring.
 // With one lane per stream the serial arithmetic of the recurrence is amortised over 32 streams (the
 // warp-per-stream kernel spends 330 warp-instructions per stream and symbol, this kernel ~65 in
@@ -48,8 +48,8 @@ constexpr int kStageAll = 2 * kStage;  // per stream and symbol (two staging war
 struct __align__(16) BatchSmem {
     uint32_t ring[kRows][kSpc];   // 40 KB
     double2 part[4][3][kSpc];     // [warp][E,O,L][stream] interpolated partial gates, 6 KB
-    double zq[2][4][kSpc];        // [tone][z.r, z.i, q.r, q.i][stream], 2 KB
-    double xch[10][kSpc];         // loop-phase exchange: 0-6 tone 1 -> AFC warp, 7-9 tone 2 -> timing warp
+    double zq[2][2][4][kSpc];     // [symbol parity][tone][z.r, z.i, q.r, q.i][stream], 4 KB: the AFC warp writes
+                                  // the next symbol's LO steps while the timing warp still reads this symbol's
     double frac[kSpc];            // interpolation fraction f = pos - floor(pos) of the current symbol
     int w0[kSpc];                 // row-relative sample index of window slot 0 of the current symbol
     int live[kSpc];               // stream has a symbol to demodulate
@@ -111,16 +111,19 @@ __device__ __noinline__ bool schedule_cold(DemodState& st, int mode, long long a
     return live;
 }
 
-__device__ __forceinline__ void publish_lo(BatchSmem& sm, int s, const ToneLo& t1, const ToneLo& t2) {
-    sm.zq[0][0][s] = t1.z.r; sm.zq[0][1][s] = t1.z.i; sm.zq[0][2][s] = t1.q.r; sm.zq[0][3][s] = t1.q.i;
-    sm.zq[1][0][s] = t2.z.r; sm.zq[1][1][s] = t2.z.i; sm.zq[1][2][s] = t2.q.r; sm.zq[1][3][s] = t2.q.i;
-}
-__device__ __forceinline__ void pair_barrier() {  // warps 0 and 1 only
-    asm volatile("bar.sync 1, 64;" ::: "memory");
+__device__ __forceinline__ void publish_lo(BatchSmem& sm, int par, int s, const ToneLo& t1, const ToneLo& t2) {
+    sm.zq[par][0][0][s] = t1.z.r; sm.zq[par][0][1][s] = t1.z.i; sm.zq[par][0][2][s] = t1.q.r; sm.zq[par][0][3][s] = t1.q.i;
+    sm.zq[par][1][0][s] = t2.z.r; sm.zq[par][1][1][s] = t2.z.i; sm.zq[par][1][2][s] = t2.q.r; sm.zq[par][1][3][s] = t2.q.i;
 }
 
-// combine the two halves of one tone (loop phase, warps 0 and 1)
-__device__ __forceinline__ ToneGates finish_tone(BatchSmem& sm, int s, int tone, int w0, bool first) {
+// Loop phase, combining the two halves of one tone.  The two loop warps need different things (the
+// timing chain the three gate energies of both tones, the AFC chain the on-time sums), and fetching
+// them redundantly from the helpers' partial gates is cheaper than an exchange plus a barrier.
+struct GateEnergies {
+    double eE, eO, eL;
+};
+__device__ __forceinline__ GateEnergies finish_energies(BatchSmem& sm, int par, int s, int tone, int w0, double f,
+                                                       bool first) {
     HalfGates a, b;
     double2 v;
     v = sm.part[2 * tone][0][s]; a.E = {v.x, v.y}; v = sm.part[2 * tone][1][s]; a.O = {v.x, v.y};
@@ -128,13 +131,32 @@ __device__ __forceinline__ ToneGates finish_tone(BatchSmem& sm, int s, int tone,
     v = sm.part[2 * tone + 1][0][s]; b.E = {v.x, v.y}; v = sm.part[2 * tone + 1][1][s]; b.O = {v.x, v.y};
     v = sm.part[2 * tone + 1][2][s]; b.L = {v.x, v.y};
     ToneLo t;
-    t.z = {sm.zq[tone][0][s], sm.zq[tone][1][s]};
-    t.q = {sm.zq[tone][2][s], sm.zq[tone][3][s]};
+    t.z = {sm.zq[par][tone][0][s], sm.zq[par][tone][1][s]};
+    t.q = {sm.zq[par][tone][2][s], sm.zq[par][tone][3][s]};
     t.inc = 0.0;
     cplx fix = {0.0, 0.0};
     if (first)  // early-gate clamp (:237), once per call; window n is still in the ring
-        fix = first_fix_cold(&sm.ring[w0 & (kRingRows - 1)][s], sm.frac[s], t.z);
-    return batch_finish_tone(a, b, t, fix);
+        fix = first_fix_cold(&sm.ring[w0 & (kRingRows - 1)][s], f, t.z);
+    const ToneGates g = batch_finish_tone(a, b, t, fix);
+    return {g.eE, g.eO, g.eL};
+}
+struct OnTime {
+    cplx O, z40;
+    double eO;
+};
+__device__ __forceinline__ OnTime finish_ontime(BatchSmem& sm, int par, int s, int tone) {
+    double2 v;
+    v = sm.part[2 * tone][1][s];
+    const cplx aO = {v.x, v.y};
+    v = sm.part[2 * tone + 1][1][s];
+    const cplx bO = {v.x, v.y};
+    const cplx q = {sm.zq[par][tone][2][s], sm.zq[par][tone][3][s]};
+    const cplx q2 = csqr(q);
+    OnTime o;
+    o.O = cfma(q2, bO, aO);
+    o.z40 = csqr(q2);
+    o.eO = cnorm(o.O);
+    return o;
 }
 
 }  // namespace
@@ -194,7 +216,7 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
         ToneLo t1, t2;
         batch_lo(afc.freq_offset, t1, t2);  // general version: a -o offset may exceed the fast range
         inc1 = t1.inc; inc2 = t2.inc;
-        publish_lo(sm, s, t1, t2);
+        publish_lo(sm, 0, s, t1, t2);
     }
     __syncthreads();  // state of symbol 0 published
 
@@ -221,9 +243,13 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
     int pend_idx = -1;
     const int tone = k >> 1, half = k & 1;
 
+    int par = 0;  // symbol parity: which half of zq holds the current symbol's LO steps
     while (sm.any_live) {
+        // everything the loop phase overwrites for the next symbol is read here, before the barrier
         const int lv = sm.live[s];
         const int w0 = sm.w0[s];
+        const bool first = sm.first[s] != 0;
+        const double frac = sm.frac[s];
         // ---- window phase (all four warps)
         if (lv) {
             const uint32_t* src = &sm.ring[(w0 & (kRingRows - 1)) + 30 * half][s];
@@ -232,27 +258,21 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
             for (int j = 0; j < 30; ++j) unpack_ring(src[j * kSpc], I[j], Q[j]);
             I[30] = 0.0; Q[30] = 0.0;
             if (half) unpack_ring(src[30 * kSpc], I[30], Q[30]);
-            const cplx z = {sm.zq[tone][0][s], sm.zq[tone][1][s]}, q = {sm.zq[tone][2][s], sm.zq[tone][3][s]};
-            const HalfGates g = batch_half_gates(I, Q, z, q, sm.frac[s], half);
+            const cplx z = {sm.zq[par][tone][0][s], sm.zq[par][tone][1][s]};
+            const cplx q = {sm.zq[par][tone][2][s], sm.zq[par][tone][3][s]};
+            const HalfGates g = batch_half_gates(I, Q, z, q, frac, half);
             sm.part[k][0][s] = make_double2(g.E.r, g.E.i);
             sm.part[k][1][s] = make_double2(g.O.r, g.O.i);
             sm.part[k][2][s] = make_double2(g.L.r, g.L.i);
         }
         __syncthreads();  // partial gates ready
-        const bool first = sm.first[s] != 0;
         if (k == 0) {
-            // ---- tone 1 gates, then the timing chain
+            // ---- gate energies of both tones, then the timing chain
             bool live = lv != 0;
-            ToneGates g1;
             if (live) {
-                g1 = finish_tone(sm, s, 0, w0, first);
-                sm.xch[0][s] = g1.eE; sm.xch[1][s] = g1.eO; sm.xch[2][s] = g1.eL;
-                sm.xch[3][s] = g1.O.r; sm.xch[4][s] = g1.O.i; sm.xch[5][s] = g1.z40.r; sm.xch[6][s] = g1.z40.i;
-            }
-            pair_barrier();
-            if (live) {
-                const double eE2 = sm.xch[7][s], eO2 = sm.xch[8][s], eL2 = sm.xch[9][s];
-                const double soft = batch_timing(g1.eO, eO2, g1.eE, g1.eL, eE2, eL2, timing_freq, pos, g_fm);
+                const GateEnergies g1 = finish_energies(sm, par, s, 0, w0, frac, first);
+                const GateEnergies g2 = finish_energies(sm, par, s, 1, w0, frac, first);
+                const double soft = batch_timing(g1.eO, g2.eO, g1.eE, g1.eL, g2.eE, g2.eL, timing_freq, pos, g_fm);
                 *soft_ptr++ = soft;
                 sym_in_call = 1;  // any non-zero value: the open call has produced symbols
                 // ---- next symbol of this stream
@@ -278,22 +298,20 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
             const int any = __any_sync(0xffffffffu, live);
             if (s == 0) sm.any_live = any;
         } else if (k == 1) {
-            // ---- tone 2 gates, then the AFC chain and the LO steps of the next symbol
-            ToneGates g2;
+            // ---- on-time sums of both tones, then the AFC chain and the LO steps of the next symbol
             if (lv) {
-                g2 = finish_tone(sm, s, 1, w0, first);
-                sm.xch[7][s] = g2.eE; sm.xch[8][s] = g2.eO; sm.xch[9][s] = g2.eL;
-            }
-            pair_barrier();
-            if (lv) {
-                const double eO1 = sm.xch[1][s];
-                const cplx O1 = {sm.xch[3][s], sm.xch[4][s]}, z40_1 = {sm.xch[5][s], sm.xch[6][s]};
-                batch_afc(afc, O1, z40_1, eO1, g2.O, g2.z40, g2.eO, inc1, inc2, first, afc_alpha, g_fm);
+                const OnTime o1 = finish_ontime(sm, par, s, 0), o2 = finish_ontime(sm, par, s, 1);
+                batch_afc(afc, o1.O, o1.z40, o1.eO, o2.O, o2.z40, o2.eO, inc1, inc2, first, afc_alpha, g_fm);
                 if (!first) {
                     ToneLo t1, t2;
                     batch_lo_fast(afc.freq_offset, t1, t2, g_fm);  // |freq_offset| <= 2 kHz after the AFC clamp
                     inc1 = t1.inc; inc2 = t2.inc;
-                    publish_lo(sm, s, t1, t2);
+                    publish_lo(sm, par ^ 1, s, t1, t2);
+                } else {  // no AFC update on the first symbol of a call (:289): same LO steps next symbol
+#pragma unroll
+                    for (int t = 0; t < 2; ++t)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) sm.zq[par ^ 1][t][c][s] = sm.zq[par][t][c][s];
                 }
             }
         } else {
@@ -311,6 +329,7 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
             }
         }
         __syncthreads();  // state of the next symbol published, ring advanced
+        par ^= 1;
     }
 
     // ---- persist the streams' state: warp 0 writes the record, warp 1 then patches the AFC fields
