@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(kEstThreads) est_kernel(StreamBuffers sb, Demo
     const long long row0 = sb.row_base;  // estimate always runs on samples [0, 40000)
     const uint32_t* row = sb.iq + (long long)stream * sb.stride - row0;
     const int n_blocks = (int)(n_use / kSps);
-    const int slot = threadIdx.x / kEstRoles, role = threadIdx.x % kEstRoles;
+    // role-major: a warp = one role x 32 block slots, so its lanes run the same tile loops (no divergence)
+    // and hit 32 different blocks at the same index (stride 45 double2: conflict-free 128-bit loads)
+    const int slot = threadIdx.x % kEstSlots, role = threadIdx.x / kEstSlots;
     double arA[4] = {0, 0, 0, 0}, aiA[4] = {0, 0, 0, 0}, arB[4] = {0, 0, 0, 0}, aiB[4] = {0, 0, 0, 0};
 
     for (int blk0 = 0; blk0 < n_blocks; blk0 += kEstSlots) {
