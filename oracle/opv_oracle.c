@@ -69,6 +69,72 @@ double ora_estimate_offset(const int16_t* iq, size_t n) { /* :131-202 */
     return fine_best;
 }
 
+/* ------------------------------------------------------------------ coherent (-c) */
+void ora_codemod_init(ora_codemod_t* d) { /* :367-377 */
+    memset(d, 0, sizeof(*d));
+    d->afc_alpha = 0.001; d->pll_alpha = 0.01; d->pll_beta = 0.001;
+}
+
+void ora_codemod_set_pll_bandwidth(ora_codemod_t* d, double bw) { /* :561-568 */
+    double wn = bw * TWO_PI;
+    double zeta = 0.707;
+    d->pll_alpha = 2.0 * zeta * wn / SYMBOL_RATE;
+    d->pll_beta = wn * wn / (SYMBOL_RATE * SYMBOL_RATE);
+}
+
+size_t ora_codemod_demodulate(ora_codemod_t* d, const int16_t* iq, size_t n, double* soft_out, size_t cap) { /* :450-548 */
+    size_t ns = 0;
+    double phase_inc_f1 = TWO_PI * (-FREQ_DEV + d->freq_offset) / SAMPLE_RATE;
+    double phase_inc_f2 = TWO_PI * (+FREQ_DEV + d->freq_offset) / SAMPLE_RATE;
+    for (size_t sym = 0; sym < n / ORA_SPS; ++sym) {
+        double c1r = 0, c1i = 0, c2r = 0, c2i = 0;
+        for (size_t i = 0; i < ORA_SPS; ++i) { /* :461-483 */
+            size_t idx = sym * ORA_SPS + i;
+            double a = iq[2 * idx], b = iq[2 * idx + 1];
+            double pr = cos(d->carrier_phase), pi = -sin(d->carrier_phase);
+            double xr = a * pr - b * pi, xi = a * pi + b * pr;          /* samples[idx] * phase_rot */
+            double l1c = cos(d->phase_f1), l1s = sin(d->phase_f1);
+            double l2c = cos(d->phase_f2), l2s = sin(d->phase_f2);
+            c1r += xr * l1c - xi * (-l1s);                               /* corrected * conj(lo) */
+            c1i += xr * (-l1s) + xi * l1c;
+            c2r += xr * l2c - xi * (-l2s);
+            c2i += xr * (-l2s) + xi * l2c;
+            d->phase_f1 += phase_inc_f1;
+            d->phase_f2 += phase_inc_f2;
+            d->carrier_phase += d->loop_freq;
+        }
+        while (d->phase_f1 > PI) d->phase_f1 -= TWO_PI;                  /* :486-491 */
+        while (d->phase_f1 < -PI) d->phase_f1 += TWO_PI;
+        while (d->phase_f2 > PI) d->phase_f2 -= TWO_PI;
+        while (d->phase_f2 < -PI) d->phase_f2 += TWO_PI;
+        while (d->carrier_phase > PI) d->carrier_phase -= TWO_PI;
+        while (d->carrier_phase < -PI) d->carrier_phase += TWO_PI;
+        double e1 = c1r * c1r + c1i * c1i, e2 = c2r * c2r + c2i * c2i;   /* :494-495 */
+        if (ns < cap) soft_out[ns] = c2r - c1r;                          /* :500-505 */
+        ++ns;
+        double dr = (e1 > e2) ? c1r : c2r, di = (e1 > e2) ? c1i : c2i;   /* :510 */
+        double mag = hypot(dr, di);                                      /* std::abs */
+        double phase_error = 0;
+        if (mag > 1e-10) phase_error = di / mag;                         /* :514-520 */
+        d->loop_freq += d->pll_beta * phase_error;                       /* :524-525 */
+        d->carrier_phase += d->pll_alpha * phase_error;
+        d->loop_freq = clampd(d->loop_freq, -0.1, 0.1);                  /* :528 */
+        if (sym > 0) {                                                   /* :533-541 */
+            double npi = -d->prev_im;                                    /* dominant * conj(prev_dominant) */
+            double xr = dr * d->prev_re - di * npi;
+            double xi = dr * npi + di * d->prev_re;
+            double phase_diff = atan2(xi, xr);
+            double freq_err = phase_diff * SYMBOL_RATE / TWO_PI;
+            d->freq_offset += d->afc_alpha * freq_err;
+            d->freq_offset = clampd(d->freq_offset, -2000.0, 2000.0);
+            phase_inc_f1 = TWO_PI * (-FREQ_DEV + d->freq_offset) / SAMPLE_RATE;
+            phase_inc_f2 = TWO_PI * (+FREQ_DEV + d->freq_offset) / SAMPLE_RATE;
+        }
+        d->prev_re = dr; d->prev_im = di;                                /* :543 */
+    }
+    return ns;
+}
+
 /* ------------------------------------------------------------------ A3 */
 void ora_demod_init(ora_demod_t* d) { /* :110-119 */
     memset(d, 0, sizeof(*d));
@@ -409,7 +475,19 @@ int ora_run(const ora_cfg_t* cfg, const int16_t* iq, size_t n, ora_result_t* res
     double* soft = malloc(sizeof(double) * (cap_tmp ? cap_tmp : 1));
     if (!soft) return -1;
 
-    if (!cfg->streaming) { /* :1127-1216 */
+    if (!cfg->streaming && cfg->coherent) { /* :1144-1161 */
+        ora_codemod_t cd; ora_codemod_init(&cd);
+        res->est_offset = ora_estimate_offset(iq, n);   /* CoherentMSKDemodulator::estimate_offset (:379-446) is the same search */
+        cd.freq_offset = res->est_offset;
+        cd.afc_alpha = cfg->afc_alpha;
+        ora_codemod_set_pll_bandwidth(&cd, cfg->pll_bw);
+        if (res->chunk_starts && res->cap_chunks) res->chunk_starts[0] = 0;
+        res->n_chunks = 1;
+        size_t ns = ora_codemod_demodulate(&cd, iq, n, soft, cap_tmp);
+        for (size_t i = 0; i < ns; ++i) { if (res->soft && res->n_soft < res->cap_soft) res->soft[res->n_soft] = soft[i]; res->n_soft++; }
+        feed_soft(&ctx, soft, ns);
+        d.freq_offset = cd.freq_offset;
+    } else if (!cfg->streaming) { /* :1127-1216 */
         res->est_offset = ora_estimate_offset(iq, n);
         d.freq_offset = res->est_offset;
         d.afc_alpha = cfg->afc_alpha;

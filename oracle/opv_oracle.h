@@ -46,6 +46,16 @@ double ora_estimate_offset(const int16_t* iq, size_t n);
 /* one demodulate() call (:206-329); returns number of soft symbols (may exceed cap; only cap are stored) */
 size_t ora_demodulate(ora_demod_t* d, const int16_t* iq, size_t n, double* soft_out, size_t cap);
 
+/* ---- CoherentMSKDemodulator (:365-572), the batch-only `-c` alternative ---- */
+typedef struct {
+    double freq_offset, carrier_phase, phase_f1, phase_f2, loop_freq;
+    double prev_re, prev_im;
+    double afc_alpha, pll_alpha, pll_beta;
+} ora_codemod_t;
+void ora_codemod_init(ora_codemod_t* d);                       /* :367-377 */
+void ora_codemod_set_pll_bandwidth(ora_codemod_t* d, double bw); /* :561-568 */
+size_t ora_codemod_demodulate(ora_codemod_t* d, const int16_t* iq, size_t n, double* soft_out, size_t cap); /* :450-548 */
+
 /* ---- A5: SyncTracker (:587-787) ---- */
 enum { ORA_HUNTING = 0, ORA_VERIFYING = 1, ORA_LOCKED = 2 };
 enum {
@@ -95,6 +105,8 @@ typedef struct {
     double afc_alpha;     /* -a, default 0.001 */
     int have_init_offset; /* -o (honoured only with -s, :1004 vs :1164) */
     double init_offset;
+    int coherent;         /* -c (batch only: the streaming branch returns first, :995-1125) */
+    double pll_bw;        /* -p, default 50.0 (:946) */
 } ora_cfg_t;
 
 typedef struct {

@@ -55,7 +55,8 @@ class _Event(C.Structure):
 
 class _Cfg(C.Structure):
     _fields_ = [("streaming", C.c_int), ("afc_alpha", C.c_double),
-                ("have_init_offset", C.c_int), ("init_offset", C.c_double)]
+                ("have_init_offset", C.c_int), ("init_offset", C.c_double),
+                ("coherent", C.c_int), ("pll_bw", C.c_double)]
 
 
 class _Result(C.Structure):
@@ -130,6 +131,9 @@ def ref():
         R.ref_run_soft.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_int, C.c_double,
                                    C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                    C.POINTER(C.c_double), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        R.ref_run_soft_coherent.restype = C.c_size_t
+        R.ref_run_soft_coherent.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_void_p, C.c_size_t,
+                                            C.POINTER(C.c_double), C.POINTER(C.c_double)]
         R.ref_track_decode.restype = C.c_size_t
         R.ref_track_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_size_t, C.POINTER(C.c_int)]
@@ -167,7 +171,7 @@ class RunResult:
 
 
 def run(iq: np.ndarray, streaming: bool, afc_alpha: float = 0.001, init_offset: float | None = None,
-        want_soft: bool = True) -> RunResult:
+        want_soft: bool = True, coherent: bool = False, pll_bw: float = 50.0) -> RunResult:
     """Whole chain through the C restatement (main() drivers, src/opv-demod.cpp:995-1216)."""
     a = _iq(iq)
     n = a.size // 2
@@ -187,7 +191,8 @@ def run(iq: np.ndarray, streaming: bool, afc_alpha: float = 0.001, init_offset: 
     res.soft = soft.ctypes.data if want_soft else None; res.cap_soft = caps
     res.events = C.addressof(ev); res.cap_events = cape
     res.chunk_starts = chunks.ctypes.data; res.cap_chunks = capc
-    cfg = _Cfg(int(streaming), afc_alpha, int(init_offset is not None), float(init_offset or 0.0))
+    cfg = _Cfg(int(streaming), afc_alpha, int(init_offset is not None), float(init_offset or 0.0),
+               int(coherent), float(pll_bw))
     rc = lib().ora_run(C.byref(cfg), a.ctypes.data, n, C.byref(res))
     assert rc == 0
     nf = min(res.n_frames, capf)
@@ -300,3 +305,15 @@ def ref_run_soft(iq: np.ndarray, streaming: bool, afc_alpha: float = 0.001, init
                         float(init_offset or 0.0), soft.ctypes.data, cap, C.byref(est), C.byref(ff), C.byref(tf),
                         chunks.ctypes.data, chunks.size, C.byref(nch))
     return soft[:ns].copy(), est.value, ff.value, tf.value, chunks[: nch.value].copy()
+
+
+def ref_run_soft_coherent(iq: np.ndarray, afc_alpha: float = 0.001, pll_bw: float = 50.0):
+    """Soft symbols of the reference's CoherentMSKDemodulator (-c, batch)."""
+    R = ref()
+    a = _iq(iq)
+    n = a.size // 2
+    cap = n // SPS + 16
+    soft = np.zeros(cap, np.float64)
+    est = C.c_double(); ff = C.c_double()
+    ns = R.ref_run_soft_coherent(a.ctypes.data, n, afc_alpha, pll_bw, soft.ctypes.data, cap, C.byref(est), C.byref(ff))
+    return soft[:ns].copy(), est.value, ff.value

@@ -132,6 +132,24 @@ size_t ref_run_soft(const int16_t* iq, size_t n, int streaming, double afc_alpha
     return all.size();
 }
 
+// Coherent mode (-c, batch only): src/opv-demod.cpp:1144-1161 on the reference's CoherentMSKDemodulator.
+size_t ref_run_soft_coherent(const int16_t* iq, size_t n, double afc_alpha, double pll_bw, double* soft_out,
+                             size_t cap, double* est_offset_out, double* final_freq) {
+    auto v = to_cplx(iq, n);
+    CoherentMSKDemodulator demod;
+    double est = demod.estimate_offset(v.data(), v.size());
+    demod.set_freq_offset(est);
+    demod.set_afc_bandwidth(afc_alpha);
+    demod.set_pll_bandwidth(pll_bw);
+    std::vector<double> soft;
+    demod.demodulate(v.data(), v.size(), soft);
+    size_t m = soft.size() < cap ? soft.size() : cap;
+    if (soft_out) memcpy(soft_out, soft.data(), m * sizeof(double));
+    if (est_offset_out) *est_offset_out = est;
+    if (final_freq) *final_freq = demod.get_freq_offset();
+    return soft.size();
+}
+
 // SyncTracker + FrameDecoder over a soft-symbol sequence (src/opv-demod.cpp:1186-1205).
 // The tracker's transition log goes to stderr exactly as in the reference binary.
 // frame_ready_idx[k] = symbol index at which frame k became ready; metrics[k] = Viterbi metric

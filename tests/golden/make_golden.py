@@ -42,6 +42,24 @@ def main():
                 "final_freq": float(ff),
                 "chunk_starts": [int(c) for c in chunks],
             }
+        # -c coherent mode (batch only): reference binary + CoherentMSKDemodulator through the harness
+        frames, events, rc, err = ora.run_ref_binary(iq, ["-c", "-r"])
+        summ = re.search(r"Summary: .*", err)
+        soft, est, ff = ora.ref_run_soft_coherent(iq)
+        out["cases"][f"{name}/coherent"] = {
+            "capture_sha256": hashlib.sha256(np.ascontiguousarray(iq).tobytes()).hexdigest(),
+            "n_samples": int(iq.shape[0]),
+            "n_frames": int(frames.shape[0]),
+            "frames_sha256": hashlib.sha256(frames.tobytes()).hexdigest(),
+            "events": [[int(t), int(i), int(c)] for (t, i, c) in events],
+            "exit_code": int(rc),
+            "summary": summ.group(0) if summ else None,
+            "n_soft": int(soft.size),
+            "soft_sha256": hashlib.sha256(soft.tobytes()).hexdigest(),
+            "est_offset": float(est),
+            "final_freq": float(ff),
+            "chunk_starts": [0],
+        }
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_golden.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)

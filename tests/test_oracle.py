@@ -22,7 +22,7 @@ def test_oracle_matches_reference_golden(key, cases, ora):
     iq = cases[name]
     g = GOLD[key]
     assert _sha(iq) == g["capture_sha256"], "capture generator drifted from the one the golden was made with"
-    r = ora.run(iq, mode == "stream")
+    r = ora.run(iq, mode == "stream", coherent=(mode == "coherent"))
     assert r.frames.shape[0] == g["n_frames"]
     assert _sha(r.frames) == g["frames_sha256"]                      # stdout bytes of the reference binary
     assert [[t, i, c] for (t, i, c, _, _) in r.events] == g["events"]  # its stderr transitions
@@ -81,6 +81,22 @@ def test_oracle_vs_reference_live(name, cases, ora):
         assert np.array_equal(fb, r.frames)
         assert [(t, i, c) for (t, i, c, _, _) in r.events] == evb
         soft_ref, est, ff, tf, chunks = ora.ref_run_soft(iq, streaming)
+        assert np.array_equal(soft_ref, r.soft) and est == r.est_offset and ff == r.final_freq
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "opv-demod")),
+                    reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("name", ["clean5", "awgn14", "awgn8", "cfo_p1200_delay", "dropout_long", "zeros_gap", "tiny"])
+def test_coherent_oracle_vs_reference_live(name, cases, ora):
+    """-c (CoherentMSKDemodulator, batch only): restatement bit-identical to the reference class and binary."""
+    iq = cases[name]
+    for kw in (dict(), dict(pll_bw=120.0, afc_alpha=0.002)):
+        r = ora.run(iq, False, coherent=True, **kw)
+        args = ["-c", "-r"] + (["-p", str(kw["pll_bw"]), "-a", str(kw["afc_alpha"])] if kw else [])
+        fb, evb, rc, _ = ora.run_ref_binary(iq, args)
+        assert np.array_equal(fb, r.frames)
+        assert [(t, i, c) for (t, i, c, _, _) in r.events] == evb
+        soft_ref, est, ff = ora.ref_run_soft_coherent(iq, kw.get("afc_alpha", 0.001), kw.get("pll_bw", 50.0))
         assert np.array_equal(soft_ref, r.soft) and est == r.est_offset and ff == r.final_freq
 
 
