@@ -55,6 +55,10 @@ typedef struct opvd_config {
     int32_t lanes_per_stream;  /* demodulator kernel variant: 0 = chosen from n_streams; 1, 2, 4 = lanes per stream
                                   of the lane kernels; 32 = one warp per stream (small banks, lowest per-symbol
                                   latency); 64 = batched, 32 streams per 128-thread CTA (large banks) */
+    int32_t coherent;          /* -c: CoherentMSKDemodulator (:365-572) instead of MSKDemodulatorAFC; honoured in batch
+                                  mode only, like the reference (the streaming branch returns first, :995-1125) */
+    int32_t reserved0;
+    double pll_bw_hz;          /* -p <hz>, Costas loop bandwidth (coherent only); <= 0 selects the default 50.0 (:946) */
 } opvd_config;
 
 typedef struct opvd_event {

@@ -37,7 +37,8 @@ class Config(C.Structure):
     _fields_ = [("n_streams", C.c_int32), ("mode", C.c_int32), ("afc_alpha", C.c_double),
                 ("have_init_offset", C.c_int32), ("device", C.c_int32), ("init_offset_hz", C.c_double),
                 ("max_samples", C.c_int64), ("max_symbols", C.c_int64), ("max_frames", C.c_int32),
-                ("lanes_per_stream", C.c_int32)]
+                ("lanes_per_stream", C.c_int32), ("coherent", C.c_int32), ("reserved0", C.c_int32),
+                ("pll_bw_hz", C.c_double)]
 
 
 class Event(C.Structure):

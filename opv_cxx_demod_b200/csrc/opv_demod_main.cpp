@@ -2,8 +2,8 @@
 //
 // Process contract of the reference (/root/reference/src/opv-demod.cpp:943-1217):
 //   argv    -q quiet, -r raw frames on stdout, -s streaming, -a <alpha>, -o <hz> (streaming only),
-//           -c / -p accepted (coherent mode is a batch-only alternative demodulator that is outside
-//           this build's scope: -c is reported and ignored), -h help; unknown arguments ignored
+//           -c coherent mode and -p <hz> PLL bandwidth (batch only, like the reference: with -s the streaming
+//           branch returns first), -h help; unknown arguments ignored
 //   stdin   int16 LE interleaved I/Q, read to EOF; a trailing partial sample is dropped
 //   stdout  with -r: 134-byte frames, one write + flush per frame
 //   stderr  banner, tracker transitions (always), frame boxes and summary unless -q
@@ -153,7 +153,7 @@ bool read_full(std::vector<int16_t>& buf, size_t want_samples, size_t& got_sampl
 
 int main(int argc, char* argv[]) {
     bool quiet = false, raw = false, coherent = false, streaming = false, have_init = false;
-    double afc_bw = 0.001, init_offset = 0.0;
+    double afc_bw = 0.001, init_offset = 0.0, pll_bw = 50.0;  // :945-947
     int device = -1;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "-q")) quiet = true;
@@ -161,7 +161,7 @@ int main(int argc, char* argv[]) {
         else if (!strcmp(argv[i], "-c")) coherent = true;
         else if (!strcmp(argv[i], "-s")) streaming = true;
         else if (!strcmp(argv[i], "-a") && i + 1 < argc) afc_bw = atof(argv[++i]);
-        else if (!strcmp(argv[i], "-p") && i + 1 < argc) ++i;  // PLL bandwidth: coherent mode only
+        else if (!strcmp(argv[i], "-p") && i + 1 < argc) pll_bw = atof(argv[++i]);
         else if (!strcmp(argv[i], "-o") && i + 1 < argc) { init_offset = atof(argv[++i]); have_init = true; }
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-h")) {
@@ -170,10 +170,10 @@ int main(int argc, char* argv[]) {
             fprintf(stderr, "  -q          Quiet mode\n");
             fprintf(stderr, "  -r          Raw output to stdout\n");
             fprintf(stderr, "  -s          Streaming mode (for live PlutoSDR input)\n");
-            fprintf(stderr, "  -c          Coherent mode (not available in the B200 build; ignored)\n");
+            fprintf(stderr, "  -c          Coherent mode (Costas loop, ~3dB better)\n");
             fprintf(stderr, "  -a <bw>     AFC bandwidth (default: 0.001)\n");
             fprintf(stderr, "  -o <hz>     Initial frequency offset (streaming mode)\n");
-            fprintf(stderr, "  -p <hz>     PLL bandwidth in Hz (coherent only; ignored)\n");
+            fprintf(stderr, "  -p <hz>     PLL bandwidth in Hz (default: 50, coherent only)\n");
             fprintf(stderr, "  --device n  CUDA device ordinal (extension)\n");
             fprintf(stderr, "  -h          Help\n");
             return 0;
@@ -182,11 +182,10 @@ int main(int argc, char* argv[]) {
     static char stdout_buffer[OPVD_FRAME_BYTES];
     setvbuf(stdout, stdout_buffer, _IOFBF, OPVD_FRAME_BYTES);  // one frame == one write (:978-979)
 
-    if (coherent && !streaming)
-        fprintf(stderr, "opv-demod (B200): -c coherent mode is not part of this build; using the AFC demodulator\n");
     if (!quiet) {
         fprintf(stderr, "╔═══════════════════════════════════════════════════════════════════╗\n");
-        if (streaming) fprintf(stderr, "║       OPV MSK Demodulator with AFC v1.0 (streaming)              ║\n");
+        if (coherent) fprintf(stderr, "║       OPV MSK Demodulator with Costas Loop v1.0 (coherent)       ║\n");
+        else if (streaming) fprintf(stderr, "║       OPV MSK Demodulator with AFC v1.0 (streaming)              ║\n");
         else fprintf(stderr, "║           OPV MSK Demodulator with AFC v1.0                       ║\n");
         fprintf(stderr, "╚═══════════════════════════════════════════════════════════════════╝\n\n");
     }
@@ -199,6 +198,8 @@ int main(int argc, char* argv[]) {
     cfg.have_init_offset = have_init ? 1 : 0;
     cfg.init_offset_hz = init_offset;
     cfg.device = device;
+    cfg.coherent = coherent ? 1 : 0;  // honoured in batch mode only, like the reference (:995 returns first)
+    cfg.pll_bw_hz = pll_bw;
     opvd_handle* h = nullptr;
     int rc;
 
@@ -271,6 +272,7 @@ int main(int argc, char* argv[]) {
     if ((rc = opvd_get_stream_info(h, 0, &si)) != OPVD_OK) return die(h, "info", rc);
     if (!quiet) {
         fprintf(stderr, "Estimated carrier offset: %.1f Hz\n", si.est_offset_hz);
+        if (coherent) fprintf(stderr, "PLL bandwidth: %.1f Hz\n", pll_bw);  // :1157-1158
         fprintf(stderr, "Demodulated %zu symbols, final AFC offset: %.1f Hz\n\n", (size_t)si.n_symbols, si.freq_offset_hz);
     }
     Sink sink{h, quiet, raw};

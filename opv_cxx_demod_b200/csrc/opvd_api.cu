@@ -396,8 +396,13 @@ int opvd_run(opvd_handle* h, int final_flag) {
     CK(cudaEventRecord(h->ev[0], h->st));
     launch_estimate(sb, h->d_dstate, h->d_est, h->S, h->cfg.mode, final_flag ? 1 : 0, h->st);
     CK(cudaEventRecord(h->ev[1], h->st));
-    CK(launch_demod(sb, so, h->d_dstate, h->S, h->cfg.mode, final_flag ? 1 : 0, h->cfg.afc_alpha,
-                    h->cfg.lanes_per_stream, h->d_counters, h->st));
+    if (h->cfg.coherent && h->cfg.mode == OPVD_MODE_BATCH) {
+        CK(launch_demod_coherent(sb, so, h->d_dstate, h->S, final_flag ? 1 : 0, h->cfg.afc_alpha,
+                                 h->cfg.pll_bw_hz > 0.0 ? h->cfg.pll_bw_hz : 50.0, h->d_counters, h->st));
+    } else {
+        CK(launch_demod(sb, so, h->d_dstate, h->S, h->cfg.mode, final_flag ? 1 : 0, h->cfg.afc_alpha,
+                        h->cfg.lanes_per_stream, h->d_counters, h->st));
+    }
     CK(cudaEventRecord(h->ev[2], h->st));
     launch_track(so, h->d_dstate, h->d_tstate, h->S, h->d_frec, h->max_frames, h->d_events, h->d_nevents,
                  h->max_events, h->d_tasks, h->d_ntasks, h->max_tasks, h->d_counters, h->st);

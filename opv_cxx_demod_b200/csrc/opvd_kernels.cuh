@@ -70,6 +70,11 @@ cudaError_t launch_demod_batch(const StreamBuffers& sb, const SoftBuffers& so, D
                                int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                                cudaStream_t st);
 
+// coherent mode (kernels_demod_coherent.cu): `opv-demod -c`, batch only
+cudaError_t launch_demod_coherent(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
+                                  int final_flag, double afc_alpha, double pll_bw_hz, unsigned long long* counters,
+                                  cudaStream_t st);
+
 void launch_track(const SoftBuffers& so, const DemodState* dstate, TrackState* tstate, int n_streams,
                   FrameRec* frec, int max_frames, TrackEvent* events, int32_t* n_events, int max_events,
                   FrameTask* tasks, int32_t* n_tasks, int max_tasks, unsigned long long* counters,

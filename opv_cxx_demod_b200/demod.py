@@ -38,13 +38,15 @@ class DemodBank:
 
     def __init__(self, n_streams: int, streaming: bool = False, afc_alpha: float = 0.001,
                  init_offset_hz: float | None = None, device: int = -1, max_samples: int = 0,
-                 max_symbols: int = 0, max_frames: int = 0, lanes_per_stream: int = 0):
+                 max_symbols: int = 0, max_frames: int = 0, lanes_per_stream: int = 0, coherent: bool = False,
+                 pll_bw_hz: float = 50.0):
         self._lib = capi.lib()
         self.n_streams = int(n_streams)
         self.streaming = bool(streaming)
         cfg = capi.Config(self.n_streams, MODE_STREAM if streaming else MODE_BATCH, float(afc_alpha),
                           int(init_offset_hz is not None), int(device), float(init_offset_hz or 0.0),
-                          int(max_samples), int(max_symbols), int(max_frames), int(lanes_per_stream))
+                          int(max_samples), int(max_symbols), int(max_frames), int(lanes_per_stream),
+                          int(bool(coherent)), 0, float(pll_bw_hz))
         self._h = C.c_void_p()
         capi.check(self._lib.opvd_create(C.byref(cfg), C.byref(self._h)), None, "opvd_create")
         self._keepalive = None

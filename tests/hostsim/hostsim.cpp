@@ -10,6 +10,7 @@
 #include "../../opv_cxx_demod_b200/csrc/demod_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/demod_warp_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/demod_batch_core.cuh"
+#include "../../opv_cxx_demod_b200/csrc/demod_coherent_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/est_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/track_core.cuh"
 
@@ -215,6 +216,25 @@ size_t hostsim_demod_batch(const int16_t* iq, size_t n, int mode, double afc_alp
     if (est_out) *est_out = est;
     if (final_freq) *final_freq = r.freq_offset;
     if (final_tfreq) *final_tfreq = r.timing_freq;
+    return ns;
+}
+
+// coherent mode (-c, batch only) through demod_coherent_core.cuh.  Returns number of soft symbols.
+size_t hostsim_demod_coherent(const int16_t* iq, size_t n, double afc_alpha, double pll_bw, double* soft_out, size_t cap,
+                              double* est_out, double* final_freq) {
+    const double est = hostsim_estimate(iq, n);
+    CoherentState st;
+    coherent_init(st, est, afc_alpha, pll_bw);
+    size_t ns = 0;
+    for (size_t sym = 0; sym < n / kSps; ++sym) {
+        double I[kSps], Q[kSps];
+        for (int i = 0; i < kSps; ++i) { I[i] = iq[2 * (sym * kSps + i)]; Q[i] = iq[2 * (sym * kSps + i) + 1]; }
+        const double soft = coherent_symbol(st, I, Q, sym == 0);
+        if (ns < cap) soft_out[ns] = soft;
+        ++ns;
+    }
+    if (est_out) *est_out = est;
+    if (final_freq) *final_freq = st.freq_offset;
     return ns;
 }
 

@@ -268,3 +268,46 @@ def test_resident_bank_properties_and_reference_spotcheck(pkg, ora):
     c = bank.counters()
     assert c["frames_compared"] == c["frames_decoded"]
     bank.close()
+
+
+COHERENT_HORIZON = 2000  # symbols over which the chaotic Costas/AFC trajectory is pinned (see tests/test_hostsim.py)
+
+
+@pytest.mark.parametrize("name", ["clean5", "awgn8", "cfo_p1200_delay", "zeros_gap", "tiny", "empty"])
+def test_coherent_mode_vs_oracle(name, pkg, cases, ora):
+    """opv-demod -c (CoherentMSKDemodulator, batch only): estimate identical, symbol count identical, soft symbols
+    within 1e-9 of rms over the pinned horizon.  Beyond it the reference's own loop is chaotic (it locks on no
+    capture), so only bit-identical libm could follow it."""
+    iq = cases[name]
+    ref = ora.run(iq, False, coherent=True)
+    bank = pkg.DemodBank(1, streaming=False, max_samples=max(iq.shape[0], 64), coherent=True)
+    if iq.shape[0]:
+        bank.push_iq(0, iq)
+    bank.run(final=True)
+    info = bank.stream_info(0)
+    assert info["est_offset_hz"] == ref.est_offset
+    assert info["n_symbols"] == ref.soft.size
+    soft = bank.get_soft(0)
+    assert soft.size == ref.soft.size
+    h = min(soft.size, COHERENT_HORIZON)
+    if h:
+        assert _soft_err(soft[:h], ref.soft[:h]) < 1e-9
+    if ref.soft.size <= COHERENT_HORIZON:
+        assert np.array_equal(bank.poll_frames().data.reshape(-1, 134), ref.frames.reshape(-1, 134))
+    bank.close()
+
+
+def test_cli_coherent_flags(pkg, cases, ora):
+    """-c / -p reach the coherent demodulator in batch mode and are ignored with -s, as in the reference."""
+    iq = cases["clean5"]
+    raw = np.ascontiguousarray(iq, np.int16).tobytes()
+    p = subprocess.run([pkg.CLI_PATH, "-c", "-p", "80"], input=raw, capture_output=True)
+    err = p.stderr.decode("utf-8", "replace")
+    assert "Costas Loop v1.0 (coherent)" in err and "PLL bandwidth: 80.0 Hz" in err
+    ref = ora.run(iq, False, coherent=True, pll_bw=80.0)
+    assert f"Estimated carrier offset: {ref.est_offset:.1f} Hz" in err
+    assert f"Demodulated {ref.soft.size} symbols" in err
+    # with -s the reference never looks at -c: identical to plain streaming
+    a = subprocess.run([pkg.CLI_PATH, "-s", "-r", "-q", "-c"], input=raw, capture_output=True)
+    b = subprocess.run([pkg.CLI_PATH, "-s", "-r", "-q"], input=raw, capture_output=True)
+    assert a.stdout == b.stdout and len(a.stdout) == 5 * 134 and a.returncode == b.returncode == 0
