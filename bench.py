@@ -114,6 +114,13 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _traffic(table, variant, algorithmic_bytes):
+    """DRAM bytes (read + write) of one launch of the dominant kernel: the ratio ncu measured on a captured launch
+    (profiles/roofline_traffic.json) scaled to this launch's algorithmic bytes; None without a capture."""
+    r = (table or {}).get(variant + "_dram_bytes_per_launch_per_algorithmic_byte")
+    return None if r is None else int(r * algorithmic_bytes)
+
+
 def load_profile_json(name):
     p = os.path.join(ROOT, "profiles", name)
     return json.load(open(p)) if os.path.exists(p) else None
@@ -248,7 +255,8 @@ def run_channel_bank(args, pkg, torch, dev, local_rank, rank, world, barrier, re
         "ber": (tot["bit_errors"] / (tot["frames_compared"] * 1072.0)) if tot["frames_compared"] else None,
         "roofline": {"bound": "hbm", "kernel": bank.demod_variant(), "achieved": round(ach, 2), "peak": peak,
                      "unit": "GB/s", "frac": round(ach / peak, 5), "launch_ms": round(demod_ms, 3),
-                     "algorithmic_bytes_per_launch": int(c["samples"] * 4)},
+                     "algorithmic_bytes_per_launch": int(c["samples"] * 4),
+                     "traffic": _traffic(load_profile_json("roofline_traffic.json"), bank.demod_variant(), c["samples"] * 4)},
         "note": "the estimate kernel is a fixed cost per stream (first 40,000 samples); with 14-frame captures it is a "
                 "visible share of the step, with 10-s captures it is 0.4 %",
     }
@@ -346,7 +354,7 @@ def main():
     mb = load_profile_json("microbench_r01.json")
     variant = bank.demod_variant()
     roofline = {"bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
-                "traffic": (traffic or {}).get(variant + "_dram_bytes_per_launch_per_algorithmic_byte"),
+                "traffic": _traffic(traffic, variant, counters["samples"] * 4),
                 "kernel": variant, "launch_ms": round(demod_ms, 3), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(counters["samples"] * 4),
                 "note": "1,024 streams are bound by the per-symbol latency of the serial timing/AFC recurrence "
