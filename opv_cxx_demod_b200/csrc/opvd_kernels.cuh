@@ -53,6 +53,7 @@ void launch_estimate(const StreamBuffers& sb, DemodState* dstate, double* est_ou
 // lanes_per_stream in {1, 2, 4, 32, 64}; 0 = chosen from the stream count; returns cudaError
 //   1/2/4  lane kernels (kernels_demod.cu)    32  warp per stream (kernels_demod_warp.cu)
 //   64     batched: 32 streams per 128-thread CTA (kernels_demod_batch.cu)
+//   128    pipelined batched: 2 x 32 streams per 128-thread CTA (kernels_demod_pipe.cu)
 cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                          int mode, int final_flag, double afc_alpha, int lanes_per_stream,
                          unsigned long long* counters, cudaStream_t st);
@@ -69,6 +70,11 @@ cudaError_t launch_demod_warp(const StreamBuffers& sb, const SoftBuffers& so, De
 cudaError_t launch_demod_batch(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                                int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                                cudaStream_t st);
+
+// pipelined batched variant (kernels_demod_pipe.cu); selected by launch_demod for lanes_per_stream == 128
+cudaError_t launch_demod_pipe(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
+                              int mode, int final_flag, double afc_alpha, unsigned long long* counters,
+                              cudaStream_t st);
 
 // coherent mode (kernels_demod_coherent.cu): `opv-demod -c`, batch only
 cudaError_t launch_demod_coherent(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,

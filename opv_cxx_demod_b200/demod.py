@@ -131,7 +131,8 @@ class DemodBank:
     def demod_variant(self) -> str:
         """Name of the demodulator kernel this bank runs (automatic selection resolved)."""
         lanes = int(self._lib.opvd_demod_lanes(self._h))
-        return {32: "demod_warp_kernel", 64: "demod_batch_kernel"}.get(lanes, f"demod_kernel_t(lanes={lanes})")
+        return {32: "demod_warp_kernel", 64: "demod_batch_kernel", 128: "demod_pipe_kernel"}.get(
+            lanes, f"demod_kernel_t(lanes={lanes})")
 
     # -- output --------------------------------------------------------------------------------
     def poll_frames(self, max_frames: int | None = None) -> Frames:
