@@ -40,29 +40,30 @@ OPVD_HD cplx horner10(const double* I, const double* Q, cplx z) {
     return g;
 }
 
-// one tone, one window half: I/Q = the half's 30 samples (slots 30h .. 30h+29) plus, for h = 1,
-// slot 60 in I[30]/Q[30].  Returns the interpolated partial gates.
-OPVD_HD HalfGates batch_half_gates(const double* I, const double* Q, cplx z, cplx q, double f, int half) {
-    const cplx A = horner10(I, Q, z), B = horner10(I + 10, Q + 10, z), C = horner10(I + 20, Q + 20, z);
+// one tone, one window half, from the half's three block sums A, B, C (slots 30h.., 30h+10.., 30h+20..) and
+// the three raw samples its edge terms need: e0, e1, e2 = slots 0, 10, 20 (h = 0) or 40, 50, 60 (h = 1).
+// Returns the interpolated partial gates.
+OPVD_HD HalfGates half_gates_from_blocks(cplx A, cplx B, cplx C, cplx e0, cplx e1, cplx e2, cplx z, cplx q, double f,
+                                         int half) {
     HalfGates g, d;  // partial gate sums and their edge terms
     if (half == 0) {
         g.L = C;
         g.O = cfma(q, C, B);
         g.E = cfma(q, g.O, A);
-        d.E = {-I[0], -Q[0]};
-        d.O = {-I[10], -Q[10]};
-        d.L = {-I[20], -Q[20]};
+        d.E = {-e0.r, -e0.i};
+        d.O = {-e1.r, -e1.i};
+        d.L = {-e2.r, -e2.i};
     } else {
         g.E = A;
         g.O = cfma(q, B, A);
         g.L = cfma(q, cfma(q, C, B), A);
         const cplx q2 = csqr(q), q3 = cmul(q2, q);
-        d.E = {q.r * I[10], q.i * I[10]};
-        d.E = {fma(-q.i, Q[10], d.E.r), fma(q.r, Q[10], d.E.i)};     // s40 * q
-        d.O = {q2.r * I[20], q2.i * I[20]};
-        d.O = {fma(-q2.i, Q[20], d.O.r), fma(q2.r, Q[20], d.O.i)};   // s50 * q^2
-        d.L = {q3.r * I[30], q3.i * I[30]};
-        d.L = {fma(-q3.i, Q[30], d.L.r), fma(q3.r, Q[30], d.L.i)};   // s60 * q^3
+        d.E = {q.r * e0.r, q.i * e0.r};
+        d.E = {fma(-q.i, e0.i, d.E.r), fma(q.r, e0.i, d.E.i)};     // s40 * q
+        d.O = {q2.r * e1.r, q2.i * e1.r};
+        d.O = {fma(-q2.i, e1.i, d.O.r), fma(q2.r, e1.i, d.O.i)};   // s50 * q^2
+        d.L = {q3.r * e2.r, q3.i * e2.r};
+        d.L = {fma(-q3.i, e2.i, d.L.r), fma(q3.r, e2.i, d.L.i)};   // s60 * q^3
     }
     auto interp = [&](cplx Cg, cplx dX) {
         const cplx S = {Cg.r + dX.r, Cg.i + dX.i};
@@ -74,6 +75,13 @@ OPVD_HD HalfGates batch_half_gates(const double* I, const double* Q, cplx z, cpl
     o.O = interp(g.O, d.O);
     o.L = interp(g.L, d.L);
     return o;
+}
+
+// the same from the half's 30 samples I/Q (slots 30h .. 30h+29) plus, for h = 1, slot 60 in I[30]/Q[30]
+OPVD_HD HalfGates batch_half_gates(const double* I, const double* Q, cplx z, cplx q, double f, int half) {
+    const cplx A = horner10(I, Q, z), B = horner10(I + 10, Q + 10, z), C = horner10(I + 20, Q + 20, z);
+    const cplx s0 = {I[0], Q[0]}, s10 = {I[10], Q[10]}, s20 = {I[20], Q[20]}, s30 = {I[30], Q[30]};
+    return half_gates_from_blocks(A, B, C, half ? s10 : s0, half ? s20 : s10, half ? s30 : s20, z, q, f, half);
 }
 
 // tone step z = exp(-j*inc_t) and block step q = z^10 from the AFC offset (:210-211, :305-306)

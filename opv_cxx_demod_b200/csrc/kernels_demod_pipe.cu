@@ -3,17 +3,21 @@
 //
 // The batched kernel alternates a window phase and a loop phase per symbol, so at any time about half
 // of its warps wait at a barrier, and its window warps convert every sample once per tone.  Here a CTA
-// of 128 threads owns TWO groups of 32 streams and its four warps are specialised:
+// of 256 threads (one per SM) is two independent QUADS of four warps; a quad owns TWO groups of 32
+// streams and its warps are specialised:
 //   warps W0, W1  window workers: half h of the 60-sample window for BOTH tones (samples are loaded and
 //                 converted once), then — after a two-warp named barrier — W_h combines the halves of
 //                 tone h and publishes its gate energies / on-time sum;
 //   warp  T       timing chain of the group whose window finished one period earlier (soft decision,
-//                 TED, timing loop, call schedule, soft store) and that group's ring staging (cp.async
-//                 straight from HBM into the transposed ring, no registers, a full symbol to land);
+//                 TED, timing loop, call schedule, soft store) and that group's ring staging (128-bit
+//                 global loads of whole 32-byte sectors, issued one visit = one symbol before they are
+//                 stored into the transposed ring; 4-byte cp.async was measured at 32 shared-memory
+//                 wavefronts per instruction and made the first version LSU-bound);
 //   warp  A       AFC chain of the same group (phase detector, AFC loop, LO steps of its next symbol).
-// Period p: window(group p & 1) runs while loop(group ~p & 1) runs; one CTA barrier per period.  Every
-// warp is busy in every period, and the instruction count per stream and symbol drops by ~30 %.
-// Lane = stream everywhere, so there is still no intra-warp exchange.
+// Period p: window(group p & 1) runs while loop(group ~p & 1) runs; one quad barrier (named, 128
+// threads) per period.  Warps land on SM sub-partitions by warp id, so quad 0 uses the role order
+// W0 W1 T A and quad 1 the order T A W0 W1: every sub-partition's FP64 pipe gets exactly one window
+// worker and one loop warp.  Lane = stream everywhere, so there is still no intra-warp exchange.
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -26,15 +30,19 @@ namespace opvd {
 namespace {
 
 constexpr int kSpc = 32;            // streams per group
-constexpr int kThreads = 128;
+constexpr int kQuads = 2;           // quads per CTA
+constexpr int kGroups = 2 * kQuads; // stream groups per CTA
+constexpr int kQuadThreads = 128;  // W0 W1 T A
+constexpr int kThreads = kQuadThreads * kQuads + 32 * kQuads;  // + one staging warp per quad
 constexpr int kRingRows = 256;      // samples per stream resident in shared memory (power of two)
 constexpr int kMirrorRows = 64;     // rows 0..63 repeated after row 255: a 61-row window never wraps
 constexpr int kRows = kRingRows + kMirrorRows;
-constexpr int kSub = 8;             // samples per 32-byte sector
-constexpr int kStageAll = 6 * kSub; // samples staged per stream and symbol
+constexpr int kSub = 8;             // samples per 32-byte sector (2 x LDG.128)
+constexpr int kStageVec = 12;       // uint4 per stream and visit
+constexpr int kStageAll = 4 * kStageVec;  // samples staged per stream and symbol (48)
 
 struct __align__(16) GroupSmem {
-    uint32_t ring[kRows][kSpc];     // transposed sample ring, 40 KB
+    uint32_t ring[kRows][kSpc];     // transposed sample ring (Q offset-binary), 40 KB
     double2 part[2][2][3][kSpc];    // [tone][half][E,O,L] interpolated partial gates
     double tg[2][7][kSpc];          // per tone: eE, eO, eL, O.r, O.i, z40.r, z40.i
     double zq[2][4][kSpc];          // [tone][z.r, z.i, q.r, q.i]: LO steps of the group's next window
@@ -43,23 +51,27 @@ struct __align__(16) GroupSmem {
     int live[kSpc], first[kSpc];    // next window: stream has a symbol / it is the first of a call
     int sym_live[kSpc], sym_first[kSpc];  // the same two for the symbol the loop warps are working on
     int any_live;                   // some stream of the group has a next window
-    int ran;                        // the window workers processed the group in the previous period
+    int ran;                        // the window workers processed the group in their last period
 };
 struct __align__(16) PipeSmem {
-    GroupSmem g[2];
+    GroupSmem g[kGroups];
 };
+static_assert(sizeof(PipeSmem) <= 227 * 1024, "pipe kernel shared memory");
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+// named barriers: 1 + 2*quad = the quad and its staging warp (160 threads), 2 + 2*quad = its two window workers
+__device__ __forceinline__ void quad_barrier(int id) { asm volatile("bar.sync %0, 160;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+constexpr uint32_t kQBias = 0x80000000u;
+// ring word (I raw, Q offset-binary) -> doubles.  I through I2F.F64.S16 (XU pipe), Q through the 2^52
+// bias trick (integer pipe + one DADD on the FP64 pipe).
+__device__ __forceinline__ void unpack_ring(uint32_t w, double& I, double& Q) {
+    I = (double)(int16_t)(w & 0xFFFFu);
+    Q = __hiloint2double(0x43300000, (int)(w >> 16)) - 4503599627403264.0;  // 2^52 + 2^15
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void pair_barrier() { asm volatile("bar.sync 1, 64;" ::: "memory"); }  // W0 + W1
 
 __device__ __noinline__ cplx first_fix_cold(const uint32_t* win, double f, cplx z) {
-    return first_symbol_fix_w([&](int kk) { return win[kk * kSpc]; }, f, z);
+    return first_symbol_fix_w([&](int kk) { return win[kk * kSpc] ^ kQBias; }, f, z);
 }
 __device__ __noinline__ bool schedule_cold(DemodState& st, int mode, long long avail, bool final_flag) {
     double pos = st.pos;
@@ -68,36 +80,43 @@ __device__ __noinline__ bool schedule_cold(DemodState& st, int mode, long long a
     return live;
 }
 
-// ---- ring staging: up to 48 samples of one stream, asynchronously (timing warp)
-__device__ __forceinline__ void stage_async(GroupSmem& sm, int s, const uint32_t* __restrict__ row, int stride, int& fill,
-                                            int w0) {
-    if (fill + kStageAll <= w0 + kRingRows) {
+// ---- ring staging (timing warp): 48 samples of one stream per visit, through registers
+// rows are 16-byte aligned and a multiple of 4 samples long, so only the last chunk of a row can be partial
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {  // read-once data: keep it out of the (tiny) L1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stage_load(const uint32_t* row, int idx, int stride, uint4 (&v)[kStageVec]) {
+    const uint4* p = reinterpret_cast<const uint4*>(row + idx);
+    if (idx + kStageAll <= stride) {
 #pragma unroll
-        for (int c = 0; c < kStageAll / kSub; ++c) {
-            const int idx = fill + kSub * c;
-            if (idx + kSub <= stride) {
-                const int r = idx & (kRingRows - 1);
-                const uint32_t dst = smem_u32(&sm.ring[r][s]);
+        for (int j = 0; j < kStageVec; ++j) v[j] = ldg_stream(p + j);
+    } else {
 #pragma unroll
-                for (int j = 0; j < kSub; ++j) cp_async4(dst + j * (kSpc * 4), row + idx + j);
-                if (r < kMirrorRows) {
+        for (int j = 0; j < kStageVec; ++j) v[j] = (idx + 4 * j + 4 <= stride) ? ldg_stream(p + j) : make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+__device__ __forceinline__ void stage_store(GroupSmem& sm, int s, int idx, const uint4 (&v)[kStageVec]) {
 #pragma unroll
-                    for (int j = 0; j < kSub; ++j) cp_async4(dst + (kRingRows + j) * (kSpc * 4), row + idx + j);
-                }
-            } else if (idx < stride) {  // last, partial sector of a row
-                for (int j = 0; idx + j < stride; ++j) {
-                    const int r = (idx + j) & (kRingRows - 1);
-                    cp_async4(smem_u32(&sm.ring[r][s]), row + idx + j);
-                    if (r < kMirrorRows) cp_async4(smem_u32(&sm.ring[kRingRows + r][s]), row + idx + j);
-                }
-            }
+    for (int c = 0; c < kStageVec / 2; ++c) {
+        const int row = (idx + kSub * c) & (kRingRows - 1);
+        const uint4 a = v[2 * c], b = v[2 * c + 1];
+        // the ring holds Q with its sign bit flipped (offset binary): unpack_ring() needs no per-use XOR
+        const uint32_t w[8] = {a.x ^ kQBias, a.y ^ kQBias, a.z ^ kQBias, a.w ^ kQBias,
+                               b.x ^ kQBias, b.y ^ kQBias, b.z ^ kQBias, b.w ^ kQBias};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm.ring[row + j][s] = w[j];
+        if (row < kMirrorRows) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sm.ring[kRingRows + row + j][s] = w[j];
         }
-        fill += kStageAll;
     }
 }
 
 // ---- window worker: half `half` of the window, both tones; then the halves of tone `half` are combined
-__device__ __forceinline__ void window_role(GroupSmem& sm, int s, int half) {
+__device__ __forceinline__ void window_role(GroupSmem& sm, int s, int half, int pbar) {
     if (!sm.any_live) {  // uniform
         if (half == 0 && s == 0) sm.ran = 0;
         return;
@@ -112,22 +131,40 @@ __device__ __forceinline__ void window_role(GroupSmem& sm, int s, int half) {
     }
     const uint32_t* win = &sm.ring[w0 & (kRingRows - 1)][s];
     if (lv) {
+        // Two passes keep the register footprint small (168 registers at 320 threads, and a spill is an L2 round
+        // trip here): blocks 0-1 of the half for both tones (8 independent Horner chains), then block 2.
         const uint32_t* src = win + 30 * half * kSpc;
-        double I[31], Q[31];  // slots 30h .. 30h+29, and slot 60 for the late gate's edge term (h = 1)
+        const cplx z1 = {sm.zq[0][0][s], sm.zq[0][1][s]}, z2 = {sm.zq[1][0][s], sm.zq[1][1][s]};
+        cplx A1, B1, C1, A2, B2, C2, s0, s10, s20, s30;
+        {
+            double I[20], Q[20];
 #pragma unroll
-        for (int j = 0; j < 30; ++j) unpack_iq_mixed(src[j * kSpc], I[j], Q[j]);
-        I[30] = 0.0; Q[30] = 0.0;
-        if (half) unpack_iq(src[30 * kSpc], I[30], Q[30]);
-#pragma unroll
-        for (int tone = 0; tone < 2; ++tone) {
-            const cplx z = {sm.zq[tone][0][s], sm.zq[tone][1][s]}, q = {sm.zq[tone][2][s], sm.zq[tone][3][s]};
-            const HalfGates g = batch_half_gates(I, Q, z, q, f, half);
-            sm.part[tone][half][0][s] = make_double2(g.E.r, g.E.i);
-            sm.part[tone][half][1][s] = make_double2(g.O.r, g.O.i);
-            sm.part[tone][half][2][s] = make_double2(g.L.r, g.L.i);
+            for (int j = 0; j < 20; ++j) unpack_ring(src[j * kSpc], I[j], Q[j]);
+            A1 = horner10(I, Q, z1); B1 = horner10(I + 10, Q + 10, z1);
+            A2 = horner10(I, Q, z2); B2 = horner10(I + 10, Q + 10, z2);
+            s0 = {I[0], Q[0]}; s10 = {I[10], Q[10]};
         }
+        {
+            double I[11], Q[11];  // slots 30h+20 .. 30h+29, and slot 60 for the late gate's edge term (h = 1)
+#pragma unroll
+            for (int j = 0; j < 10; ++j) unpack_ring(src[(20 + j) * kSpc], I[j], Q[j]);
+            I[10] = 0.0; Q[10] = 0.0;
+            if (half) unpack_ring(src[30 * kSpc], I[10], Q[10]);
+            C1 = horner10(I, Q, z1); C2 = horner10(I, Q, z2);
+            s20 = {I[0], Q[0]}; s30 = {I[10], Q[10]};
+        }
+        const cplx e0 = half ? s10 : s0, e1 = half ? s20 : s10, e2 = half ? s30 : s20;
+        const cplx q1 = {sm.zq[0][2][s], sm.zq[0][3][s]}, q2 = {sm.zq[1][2][s], sm.zq[1][3][s]};
+        const HalfGates ga = half_gates_from_blocks(A1, B1, C1, e0, e1, e2, z1, q1, f, half);
+        sm.part[0][half][0][s] = make_double2(ga.E.r, ga.E.i);
+        sm.part[0][half][1][s] = make_double2(ga.O.r, ga.O.i);
+        sm.part[0][half][2][s] = make_double2(ga.L.r, ga.L.i);
+        const HalfGates gb = half_gates_from_blocks(A2, B2, C2, e0, e1, e2, z2, q2, f, half);
+        sm.part[1][half][0][s] = make_double2(gb.E.r, gb.E.i);
+        sm.part[1][half][1][s] = make_double2(gb.O.r, gb.O.i);
+        sm.part[1][half][2][s] = make_double2(gb.L.r, gb.L.i);
     }
-    pair_barrier();
+    pair_barrier(pbar);
     if (lv) {
         const int tone = half;
         HalfGates a, b;
@@ -149,22 +186,22 @@ __device__ __forceinline__ void window_role(GroupSmem& sm, int s, int half) {
 }
 
 // ---- timing warp state of one group
+// (the DemodState record itself is a separate object: the out-of-line scheduler takes its address, which
+// pins it in local memory, and with ~215 KB of shared memory carved out of L1 every local access is an
+// L2 round trip — nothing the hot path touches may share an object with it)
 struct TimingState {
-    DemodState st;  // local memory: only the out-of-line scheduler touches it
     double pos, timing_freq, call_len_d;
     long long avail, n_sym0, origin0;
     double* soft_row;
     double* soft_ptr;
-    const uint32_t* row;
-    int origin_rel, sym_in_call, w0, fill, stride;
+    int origin_rel, sym_in_call;
     bool live, valid;
 };
 
 __device__ __forceinline__ void timing_publish(GroupSmem& sm, int s, TimingState& t) {
     if (t.live) {
         const int b = __double2int_rz(t.pos);  // pos >= 0: truncation == floor (:125)
-        t.w0 = t.origin_rel + b - kWinLead;
-        sm.w0[s] = t.w0;
+        sm.w0[s] = t.origin_rel + b - kWinLead;
         sm.frac[s] = t.pos - (double)b;
         sm.first[s] = t.sym_in_call == 0;
     }
@@ -173,69 +210,88 @@ __device__ __forceinline__ void timing_publish(GroupSmem& sm, int s, TimingState
     if (s == 0) sm.any_live = any;
 }
 
-__device__ __forceinline__ void timing_init(GroupSmem& sm, int s, TimingState& t, const StreamBuffers& sb,
+__device__ __forceinline__ void timing_init(GroupSmem& sm, int s, TimingState& t, DemodState& st, const StreamBuffers& sb,
                                             const SoftBuffers& so, const DemodState* dstate, int stream, bool valid,
                                             int mode, int final_flag) {
     t.valid = valid;
-    t.st = dstate[stream];
+    st = dstate[stream];
     t.avail = sb.avail[stream];
-    t.row = sb.iq + (long long)stream * sb.stride;
-    t.stride = (int)sb.stride;
     t.soft_row = so.soft + (long long)stream * so.stride - so.base;
-    t.soft_ptr = t.soft_row + t.st.n_sym;
-    t.n_sym0 = t.st.n_sym; t.origin0 = t.st.origin;
-    t.timing_freq = t.st.timing_freq;
-    t.live = valid && schedule_cold(t.st, mode, t.avail, final_flag != 0);
-    t.pos = t.st.pos;
-    t.sym_in_call = t.st.sym_in_call;
-    t.call_len_d = (double)t.st.call_len;
-    t.origin_rel = (int)(t.st.origin - sb.row_base);
-    t.w0 = 0;
+    t.soft_ptr = t.soft_row + st.n_sym;
+    t.n_sym0 = st.n_sym; t.origin0 = st.origin;
+    t.timing_freq = st.timing_freq;
+    t.live = valid && schedule_cold(st, mode, t.avail, final_flag != 0);
+    t.pos = st.pos;
+    t.sym_in_call = st.sym_in_call;
+    t.call_len_d = (double)st.call_len;
+    t.origin_rel = (int)(st.origin - sb.row_base);
+    sm.w0[s] = 0;
     timing_publish(sm, s, t);
-    t.fill = (t.w0 < 0 ? 0 : t.w0) & ~(kSub - 1);
     if (s == 0) sm.ran = 0;
 }
 
-__device__ __forceinline__ void timing_role(GroupSmem& sm, int s, TimingState& t, long long row0, int mode, int final_flag) {
-    if (!sm.ran) {  // uniform: nothing to do for this group, but keep the cp.async groups alternating between the
-        cp_async_wait<1>();  // two stream groups (the other group's wait<1> counts on it)
-        cp_async_commit();
-        return;
-    }
-    if (sm.sym_live[s]) {
+__device__ __forceinline__ void timing_role(GroupSmem& sm, int s, TimingState& t, DemodState& st, long long row0, int mode,
+                                            int final_flag) {
+    if (!sm.ran) return;  // uniform: the group's window did not run, nothing to do
+    const int sym_live = sm.sym_live[s];
+    if (sym_live) {
         const double soft = batch_timing(sm.tg[0][1][s], sm.tg[1][1][s], sm.tg[0][0][s], sm.tg[0][2][s], sm.tg[1][0][s],
                                          sm.tg[1][2][s], t.timing_freq, t.pos, g_fm);
         *t.soft_ptr++ = soft;
         t.sym_in_call = 1;  // any non-zero value: the open call has produced symbols
         if (!((t.pos + 40.0) + 10.0 < t.call_len_d)) {  // :221 fails: close the call, maybe open the next
-            t.st.n_sym = (long long)(t.soft_ptr - t.soft_row);
-            t.st.sym_in_call = t.sym_in_call;
-            t.st.pos = t.pos;
-            t.live = schedule_cold(t.st, mode, t.avail, final_flag != 0);
-            t.pos = t.st.pos;
-            t.sym_in_call = t.st.sym_in_call;
-            t.call_len_d = (double)t.st.call_len;
-            t.origin_rel = (int)(t.st.origin - row0);
+            st.n_sym = (long long)(t.soft_ptr - t.soft_row);
+            st.sym_in_call = t.sym_in_call;
+            st.pos = t.pos;
+            t.live = schedule_cold(st, mode, t.avail, final_flag != 0);
+            t.pos = st.pos;
+            t.sym_in_call = st.sym_in_call;
+            t.call_len_d = (double)st.call_len;
+            t.origin_rel = (int)(st.origin - row0);
         }
     }
-    const int w0_sym = t.w0;  // window of the symbol just finished: everything older is dead
     timing_publish(sm, s, t);
-    // staging: the batch requested two visits ago has landed; request the next one
-    cp_async_wait<1>();
-    if (sm.sym_live[s]) stage_async(sm, s, t.row, t.stride, t.fill, w0_sym);
-    cp_async_commit();
 }
 
-__device__ __forceinline__ void timing_finish(TimingState& t, DemodState* dstate, int stream,
+// ---- staging warp of a quad: keeps the two groups' rings ahead of their windows.  In every period it first
+// stores the 48 samples per stream it requested one period ago (for the group whose window ran then; the
+// rows it overwrites hold samples older than that window, so nobody reads them any more), then requests
+// the next 48 for the group whose window runs NOW (its w0/live are stable: the timing warp is on the other
+// group).  The stores are complete before that group's next window starts, one barrier later.  A dedicated
+// warp, because a warp with global loads in flight shares its register scoreboards with them: when the
+// timing warp staged, its visit took a full HBM latency (measured).
+struct StageState {
+    const uint32_t* row;
+    int fill;
+};
+typedef uint4 PendRegs[kStageVec];
+__device__ __forceinline__ void stage_init(GroupSmem& sm, int s, StageState& g, PendRegs& pend, const StreamBuffers& sb,
+                                           int stream) {
+    g.row = sb.iq + (long long)stream * sb.stride;
+    const int stride = (int)sb.stride, w0 = sm.w0[s];
+    g.fill = (w0 < 0 ? 0 : w0) & ~(kSub - 1);
+    if (sm.live[s]) {  // prime the ring: everything up to w0 + 208..
+#pragma unroll 1
+        while (g.fill + kStageAll <= w0 + kRingRows) {
+            if (g.fill < stride) {
+                stage_load(g.row, g.fill, stride, pend);
+                stage_store(sm, s, g.fill, pend);
+            }
+            g.fill += kStageAll;
+        }
+    }
+}
+
+__device__ __forceinline__ void timing_finish(TimingState& t, DemodState& st, DemodState* dstate, int stream,
                                               unsigned long long* counters) {
     if (!t.valid) return;
-    t.st.n_sym = (long long)(t.soft_ptr - t.soft_row);
-    t.st.sym_in_call = t.sym_in_call;
-    t.st.pos = t.pos; t.st.timing_freq = t.timing_freq;
-    dstate[stream] = t.st;
-    unsigned long long dsym = (unsigned long long)(t.st.n_sym - t.n_sym0);
-    unsigned long long dsmp = (unsigned long long)(t.st.origin - t.origin0);
-    if (t.st.flags & kFlagDone) dsmp = (unsigned long long)(t.avail - t.origin0);
+    st.n_sym = (long long)(t.soft_ptr - t.soft_row);
+    st.sym_in_call = t.sym_in_call;
+    st.pos = t.pos; st.timing_freq = t.timing_freq;
+    dstate[stream] = st;
+    unsigned long long dsym = (unsigned long long)(st.n_sym - t.n_sym0);
+    unsigned long long dsmp = (unsigned long long)(st.origin - t.origin0);
+    if (st.flags & kFlagDone) dsmp = (unsigned long long)(t.avail - t.origin0);
     if (dsym) atomicAdd(&counters[kCtrSymbols], dsym);
     if (dsmp) atomicAdd(&counters[kCtrSamples], dsmp);
 }
@@ -278,63 +334,131 @@ __device__ __forceinline__ void afc_finish(const AfcState& a, DemodState* dstate
     d->freq_offset = a.afc.freq_offset; d->ph1 = a.afc.ph1; d->ph2 = a.afc.ph2; d->p1 = a.afc.p1; d->p2 = a.afc.p2;
 }
 
+template <typename T>
+__device__ __forceinline__ void swap_regs(T& a, T& b) { const T t = a; a = b; b = t; }
+
 }  // namespace
 
-__global__ void __launch_bounds__(kThreads, 2)
+// Code size matters as much as the schedule here: the ten warps of a CTA run five different loops, and
+// the SM's instruction cache (L1.5, 32 KB) must hold all of them — a version with one inlined copy of each
+// role per group and quad (128 KB of SASS) spent 30-60 % of its issue slots waiting for instructions.  So
+// every role has ONE copy of its loop body; the two groups alternate through a pointer swap (window and
+// staging warps) plus a register swap of the per-group loop state (timing and AFC warps).
+__global__ void __launch_bounds__(kThreads, 1)
 demod_pipe_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
                   int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PipeSmem& sm = *reinterpret_cast<PipeSmem*>(smem_raw);
-    // roles rotate with the CTA index so that co-resident CTAs spread the heavy roles over the SM sub-partitions
-    const int s = threadIdx.x & 31, role = ((threadIdx.x >> 5) + blockIdx.x) & 3;  // 0,1: window halves; 2: timing; 3: AFC
-    const int raw0 = blockIdx.x * (2 * kSpc) + s, raw1 = raw0 + kSpc;
+    const int s = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool stager = warp >= 4 * kQuads;
+    const int quad = stager ? warp - 4 * kQuads : warp >> 2;
+    // roles 0,1: window halves; 2: timing; 3: AFC; 4: staging.  Quad 1 is rotated by two warps so that each
+    // SM sub-partition (warp id mod 4) hosts one window worker and one loop warp.
+    const int role = stager ? 4 : ((warp & 3) + 2 * quad) & 3;
+    const int qbar = 1 + 2 * quad, pbar = 2 + 2 * quad;
+    GroupSmem* gw = &sm.g[2 * quad];  // group whose WINDOW runs in the current period (period 0: the quad's first)
+    GroupSmem* gl = gw + 1;           // group whose LOOP runs in the current period
+    const int raw0 = (blockIdx.x * kGroups + 2 * quad) * kSpc + s, raw1 = raw0 + kSpc;
     const bool valid0 = raw0 < n_streams, valid1 = raw1 < n_streams;
     const int stream0 = valid0 ? raw0 : n_streams - 1, stream1 = valid1 ? raw1 : n_streams - 1;
     const long long row0 = sb.row_base;
 
-    TimingState t0, t1;
-    AfcState a0, a1;
-    if (role == 2) {
-        timing_init(sm.g[0], s, t0, sb, so, dstate, stream0, valid0, mode, final_flag);
-        timing_init(sm.g[1], s, t1, sb, so, dstate, stream1, valid1, mode, final_flag);
+    // Period p: window of gw, loop of gl, then the two swap.  The exit test at the top of a period reads
+    // only flags written during the PREVIOUS period and not rewritten in this one (gl->ran by W0,
+    // gw->any_live by T), so a warp that is already inside the period cannot change what a slower warp
+    // still has to read.  It is complete: !gl->ran means gl's window found gl->any_live == 0, which T
+    // (skipping gl from now on) never sets again, and gw->any_live == 0 was written by the visit of T that
+    // consumed gw's last window.  Periods 0 and 1 start the pipeline and are not tested.
+#define OPVD_PIPE_EXIT(p) ((p) >= 2 && !gl->ran && !gw->any_live)
+
+    if (role < 2) {
+        quad_barrier(qbar);  // loop state of symbol 0 published
+        quad_barrier(qbar);  // rings primed
+#pragma unroll 1
+        for (int p = 0;; ++p) {
+            if (OPVD_PIPE_EXIT(p)) break;
+            window_role(*gw, s, role, pbar);
+            quad_barrier(qbar);
+            swap_regs(gw, gl);
+        }
+        quad_barrier(qbar);
+    } else if (role == 2) {
+        TimingState tw, tl;   // state of gw's / gl's streams
+        DemodState st0, st1;  // local memory: only the out-of-line scheduler touches them
+        DemodState* stw = &st0;
+        DemodState* stl = &st1;
+        int strw = stream0, strl = stream1;
+        timing_init(*gw, s, tw, st0, sb, so, dstate, stream0, valid0, mode, final_flag);
+        timing_init(*gl, s, tl, st1, sb, so, dstate, stream1, valid1, mode, final_flag);
+        quad_barrier(qbar);
+        quad_barrier(qbar);
+#pragma unroll 1
+        for (int p = 0;; ++p) {
+            if (OPVD_PIPE_EXIT(p)) break;
+            timing_role(*gl, s, tl, *stl, row0, mode, final_flag);
+            quad_barrier(qbar);
+            swap_regs(gw, gl); swap_regs(tw, tl); swap_regs(stw, stl); swap_regs(strw, strl);
+        }
+        // ---- persist: the timing warp writes the records, the AFC warp then patches its fields
+        timing_finish(tw, *stw, dstate, strw, counters);
+        timing_finish(tl, *stl, dstate, strl, counters);
+        quad_barrier(qbar);
     } else if (role == 3) {
-        afc_init(sm.g[0], s, a0, dstate, stream0);
-        afc_init(sm.g[1], s, a1, dstate, stream1);
-    }
-    __syncthreads();
-    if (role == 2) {  // prime both rings: everything up to w0 + 208..
-        if (t0.live) while (t0.fill + kStageAll <= t0.w0 + kRingRows) stage_async(sm.g[0], s, t0.row, t0.stride, t0.fill, t0.w0);
-        if (t1.live) while (t1.fill + kStageAll <= t1.w0 + kRingRows) stage_async(sm.g[1], s, t1.row, t1.stride, t1.fill, t1.w0);
-        cp_async_commit();
-        cp_async_wait<0>();
-    }
-    __syncthreads();
-
-    for (;;) {
-        if (!sm.g[0].any_live && !sm.g[1].any_live && !sm.g[0].ran && !sm.g[1].ran) break;  // uniform
-        // ---- period A: window of group 0, loop of group 1
-        if (role < 2) window_role(sm.g[0], s, role);
-        else if (role == 2) timing_role(sm.g[1], s, t1, row0, mode, final_flag);
-        else afc_role(sm.g[1], s, a1, afc_alpha);
-        __syncthreads();
-        // ---- period B: window of group 1, loop of group 0
-        if (role < 2) window_role(sm.g[1], s, role);
-        else if (role == 2) timing_role(sm.g[0], s, t0, row0, mode, final_flag);
-        else afc_role(sm.g[0], s, a0, afc_alpha);
-        __syncthreads();
-    }
-
-    // ---- persist: the timing warp writes the records, the AFC warp then patches its fields
-    if (role == 2) {
-        cp_async_wait<0>();
-        timing_finish(t0, dstate, stream0, counters);
-        timing_finish(t1, dstate, stream1, counters);
-    }
-    __syncthreads();
-    if (role == 3) {
+        AfcState aw, al;
+        afc_init(*gw, s, aw, dstate, stream0);
+        afc_init(*gl, s, al, dstate, stream1);
+        bool w_is_0 = true;
+        quad_barrier(qbar);
+        quad_barrier(qbar);
+#pragma unroll 1
+        for (int p = 0;; ++p) {
+            if (OPVD_PIPE_EXIT(p)) break;
+            afc_role(*gl, s, al, afc_alpha);
+            quad_barrier(qbar);
+            swap_regs(gw, gl); swap_regs(aw, al); w_is_0 = !w_is_0;
+        }
+        quad_barrier(qbar);
+        const AfcState& a0 = w_is_0 ? aw : al;
+        const AfcState& a1 = w_is_0 ? al : aw;
         if (valid0) afc_finish(a0, dstate, stream0);
         if (valid1) afc_finish(a1, dstate, stream1);
+    } else {
+        StageState fw, fl;
+        PendRegs pa, pb;
+        const int stride = (int)sb.stride;
+        quad_barrier(qbar);
+        stage_init(*gw, s, fw, pa, sb, stream0);
+        stage_init(*gl, s, fl, pa, sb, stream1);
+        quad_barrier(qbar);
+        // one period: FIRST request the next 48 samples of gw's streams into `ld` (a whole period to land), THEN
+        // store the 48 requested last period (in `st`, for the group that is gl now).  The other order makes the
+        // visit wait a full HBM latency for loads issued just before the previous barrier.
+        int idx_a = -1, idx_b = -1;  // >= 0: the buffer holds samples [idx, idx + 48) of a stream
+#define OPVD_STAGE_PERIOD(ld, ld_idx, st, st_idx)                                              \
+        ld_idx = -1;                                                                           \
+        if (gw->any_live) { /* uniform */                                                      \
+            if (gw->live[s] && fw.fill + kStageAll <= gw->w0[s] + kRingRows) {                 \
+                if (fw.fill < stride) {                                                        \
+                    stage_load(fw.row, fw.fill, stride, ld);                                   \
+                    ld_idx = fw.fill;                                                          \
+                }                                                                              \
+                fw.fill += kStageAll;                                                          \
+            }                                                                                  \
+        }                                                                                      \
+        if (st_idx >= 0) stage_store(*gl, s, st_idx, st);                                      \
+        quad_barrier(qbar);                                                                    \
+        swap_regs(gw, gl); swap_regs(fw, fl);
+#pragma unroll 1
+        for (int p = 0;; p += 2) {
+            if (OPVD_PIPE_EXIT(p)) break;
+            OPVD_STAGE_PERIOD(pa, idx_a, pb, idx_b)
+            if (OPVD_PIPE_EXIT(p + 1)) break;
+            OPVD_STAGE_PERIOD(pb, idx_b, pa, idx_a)
+        }
+#undef OPVD_STAGE_PERIOD
+        quad_barrier(qbar);
     }
+#undef OPVD_PIPE_EXIT
 }
 
 cudaError_t launch_demod_pipe(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
@@ -343,7 +467,8 @@ cudaError_t launch_demod_pipe(const StreamBuffers& sb, const SoftBuffers& so, De
     const size_t smem = sizeof(PipeSmem);
     cudaError_t e = cudaFuncSetAttribute(demod_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int grid = (n_streams + 2 * kSpc - 1) / (2 * kSpc);
+    const int per_cta = kGroups * kSpc;
+    const int grid = (n_streams + per_cta - 1) / per_cta;
     demod_pipe_kernel<<<grid, kThreads, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
     return cudaGetLastError();
 }
