@@ -32,11 +32,11 @@ namespace {
 constexpr int kSpc = 32;            // streams per group
 constexpr int kQuads = 2;           // quads per CTA
 constexpr int kGroups = 2 * kQuads; // stream groups per CTA
-constexpr int kQuadThreads = 128;  // W0 W1 T A
-constexpr int kThreads = kQuadThreads * kQuads + 32 * kQuads;  // + one staging warp per quad
+constexpr int kQuadWarps = 8;      // four window workers (tone x half), timing, AFC, two staging warps
+constexpr int kThreads = 32 * kQuadWarps * kQuads;
 constexpr int kRingRows = 256;      // samples per stream resident in shared memory (power of two)
-constexpr int kMirrorRows = 64;     // rows 0..63 repeated after row 255: a 61-row window never wraps
-constexpr int kRows = kRingRows + kMirrorRows;
+constexpr int kMirrorRows = 64;     // rows 0..63 are repeated after row 255 (the first 60 of them are stored):
+constexpr int kRows = kRingRows + kWin - 1;  // a 61-row window starting at row <= 255 never wraps
 constexpr int kSub = 8;             // samples per 32-byte sector (2 x LDG.128)
 constexpr int kStageVec = 12;       // uint4 per stream and visit
 constexpr int kStageAll = 4 * kStageVec;  // samples staged per stream and symbol (48)
@@ -53,13 +53,16 @@ struct __align__(16) GroupSmem {
     int any_live;                   // some stream of the group has a next window
     int ran;                        // the window workers processed the group in their last period
 };
+constexpr int kStagePitch = kStageVec + 1;  // uint4 per stream in the landing buffer: 208 B, so that the 8 lanes of
+                                            // a quarter-warp read 128-bit words from 32 different banks
 struct __align__(16) PipeSmem {
     GroupSmem g[kGroups];
+    uint4 landing[kQuads][kSpc][kStagePitch];  // transposition buffer of a quad's staging warp (linear per stream)
 };
 static_assert(sizeof(PipeSmem) <= 227 * 1024, "pipe kernel shared memory");
 
-// named barriers: 1 + 2*quad = the quad and its staging warp (160 threads), 2 + 2*quad = its two window workers
-__device__ __forceinline__ void quad_barrier(int id) { asm volatile("bar.sync %0, 160;" ::"r"(id) : "memory"); }
+// named barriers: 1 + 3*quad = the quad (256 threads), 2 + 3*quad + tone = the two window workers of a tone
+__device__ __forceinline__ void quad_barrier(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 constexpr uint32_t kQBias = 0x80000000u;
@@ -110,38 +113,39 @@ __device__ __forceinline__ void stage_store(GroupSmem& sm, int s, int idx, const
         for (int j = 0; j < 8; ++j) sm.ring[row + j][s] = w[j];
         if (row < kMirrorRows) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sm.ring[kRingRows + row + j][s] = w[j];
+            for (int j = 0; j < 8; ++j)
+                if (j < 4 || row + 8 <= kRows - kRingRows) sm.ring[kRingRows + row + j][s] = w[j];  // rows 256..315
         }
     }
 }
 
-// ---- window worker: half `half` of the window, both tones; then the halves of tone `half` are combined
-__device__ __forceinline__ void window_role(GroupSmem& sm, int s, int half, int pbar) {
+// ---- window worker (tone, half): 30 samples of the window for one tone; then the half-0 worker of the tone
+// combines the two halves and publishes the tone's gate energies / on-time sum
+__device__ __forceinline__ void window_role(GroupSmem& sm, int s, int tone, int half, int pbar) {
     if (!sm.any_live) {  // uniform
-        if (half == 0 && s == 0) sm.ran = 0;
+        if ((tone | half) == 0 && s == 0) sm.ran = 0;
         return;
     }
     const int lv = sm.live[s], w0 = sm.w0[s];
     const bool first = sm.first[s] != 0;
     const double f = sm.frac[s];
-    if (half == 0) {
+    if ((tone | half) == 0) {
         sm.sym_live[s] = lv;
         sm.sym_first[s] = first;
         if (s == 0) sm.ran = 1;
     }
     const uint32_t* win = &sm.ring[w0 & (kRingRows - 1)][s];
+    const cplx z = {sm.zq[tone][0][s], sm.zq[tone][1][s]}, q = {sm.zq[tone][2][s], sm.zq[tone][3][s]};
     if (lv) {
-        // Two passes keep the register footprint small (168 registers at 320 threads, and a spill is an L2 round
-        // trip here): blocks 0-1 of the half for both tones (8 independent Horner chains), then block 2.
+        // two passes keep the register footprint small (a spill is an L2 round trip here: nearly all of L1 is
+        // carved out as shared memory): blocks 0-1 of the half, then block 2
         const uint32_t* src = win + 30 * half * kSpc;
-        const cplx z1 = {sm.zq[0][0][s], sm.zq[0][1][s]}, z2 = {sm.zq[1][0][s], sm.zq[1][1][s]};
-        cplx A1, B1, C1, A2, B2, C2, s0, s10, s20, s30;
+        cplx A, B, C, s0, s10, s20, s30;
         {
             double I[20], Q[20];
 #pragma unroll
             for (int j = 0; j < 20; ++j) unpack_ring(src[j * kSpc], I[j], Q[j]);
-            A1 = horner10(I, Q, z1); B1 = horner10(I + 10, Q + 10, z1);
-            A2 = horner10(I, Q, z2); B2 = horner10(I + 10, Q + 10, z2);
+            A = horner10(I, Q, z); B = horner10(I + 10, Q + 10, z);
             s0 = {I[0], Q[0]}; s10 = {I[10], Q[10]};
         }
         {
@@ -150,23 +154,16 @@ __device__ __forceinline__ void window_role(GroupSmem& sm, int s, int half, int 
             for (int j = 0; j < 10; ++j) unpack_ring(src[(20 + j) * kSpc], I[j], Q[j]);
             I[10] = 0.0; Q[10] = 0.0;
             if (half) unpack_ring(src[30 * kSpc], I[10], Q[10]);
-            C1 = horner10(I, Q, z1); C2 = horner10(I, Q, z2);
+            C = horner10(I, Q, z);
             s20 = {I[0], Q[0]}; s30 = {I[10], Q[10]};
         }
-        const cplx e0 = half ? s10 : s0, e1 = half ? s20 : s10, e2 = half ? s30 : s20;
-        const cplx q1 = {sm.zq[0][2][s], sm.zq[0][3][s]}, q2 = {sm.zq[1][2][s], sm.zq[1][3][s]};
-        const HalfGates ga = half_gates_from_blocks(A1, B1, C1, e0, e1, e2, z1, q1, f, half);
-        sm.part[0][half][0][s] = make_double2(ga.E.r, ga.E.i);
-        sm.part[0][half][1][s] = make_double2(ga.O.r, ga.O.i);
-        sm.part[0][half][2][s] = make_double2(ga.L.r, ga.L.i);
-        const HalfGates gb = half_gates_from_blocks(A2, B2, C2, e0, e1, e2, z2, q2, f, half);
-        sm.part[1][half][0][s] = make_double2(gb.E.r, gb.E.i);
-        sm.part[1][half][1][s] = make_double2(gb.O.r, gb.O.i);
-        sm.part[1][half][2][s] = make_double2(gb.L.r, gb.L.i);
+        const HalfGates g = half_gates_from_blocks(A, B, C, half ? s10 : s0, half ? s20 : s10, half ? s30 : s20, z, q, f, half);
+        sm.part[tone][half][0][s] = make_double2(g.E.r, g.E.i);
+        sm.part[tone][half][1][s] = make_double2(g.O.r, g.O.i);
+        sm.part[tone][half][2][s] = make_double2(g.L.r, g.L.i);
     }
     pair_barrier(pbar);
-    if (lv) {
-        const int tone = half;
+    if (lv && half == 0) {
         HalfGates a, b;
         double2 v;
         v = sm.part[tone][0][0][s]; a.E = {v.x, v.y}; v = sm.part[tone][0][1][s]; a.O = {v.x, v.y};
@@ -174,9 +171,7 @@ __device__ __forceinline__ void window_role(GroupSmem& sm, int s, int half, int 
         v = sm.part[tone][1][0][s]; b.E = {v.x, v.y}; v = sm.part[tone][1][1][s]; b.O = {v.x, v.y};
         v = sm.part[tone][1][2][s]; b.L = {v.x, v.y};
         ToneLo t;
-        t.z = {sm.zq[tone][0][s], sm.zq[tone][1][s]};
-        t.q = {sm.zq[tone][2][s], sm.zq[tone][3][s]};
-        t.inc = 0.0;
+        t.z = z; t.q = q; t.inc = 0.0;
         cplx fix = {0.0, 0.0};
         if (first) fix = first_fix_cold(win, f, t.z);  // early-gate clamp (:237), once per call
         const ToneGates g = batch_finish_tone(a, b, t, fix);
@@ -350,12 +345,12 @@ demod_pipe_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PipeSmem& sm = *reinterpret_cast<PipeSmem*>(smem_raw);
     const int s = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool stager = warp >= 4 * kQuads;
-    const int quad = stager ? warp - 4 * kQuads : warp >> 2;
-    // roles 0,1: window halves; 2: timing; 3: AFC; 4: staging.  Quad 1 is rotated by two warps so that each
-    // SM sub-partition (warp id mod 4) hosts one window worker and one loop warp.
-    const int role = stager ? 4 : ((warp & 3) + 2 * quad) & 3;
-    const int qbar = 1 + 2 * quad, pbar = 2 + 2 * quad;
+    // Warps land on SM sub-partitions by warp id mod 4; in each quad warps 0-3 are the window workers (tone =
+    // w >> 1, half = w & 1), so every sub-partition hosts one window worker of each quad; 4 timing, 5 AFC,
+    // 6 / 7 staging of the quad's first / second group.
+    const int quad = warp / kQuadWarps;
+    const int role = warp - kQuadWarps * quad;
+    const int qbar = 1 + 3 * quad, pbar = 2 + 3 * quad + ((role >> 1) & 1);
     GroupSmem* gw = &sm.g[2 * quad];  // group whose WINDOW runs in the current period (period 0: the quad's first)
     GroupSmem* gl = gw + 1;           // group whose LOOP runs in the current period
     const int raw0 = (blockIdx.x * kGroups + 2 * quad) * kSpc + s, raw1 = raw0 + kSpc;
@@ -371,18 +366,18 @@ demod_pipe_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     // consumed gw's last window.  Periods 0 and 1 start the pipeline and are not tested.
 #define OPVD_PIPE_EXIT(p) ((p) >= 2 && !gl->ran && !gw->any_live)
 
-    if (role < 2) {
+    if (role < 4) {
         quad_barrier(qbar);  // loop state of symbol 0 published
         quad_barrier(qbar);  // rings primed
 #pragma unroll 1
         for (int p = 0;; ++p) {
             if (OPVD_PIPE_EXIT(p)) break;
-            window_role(*gw, s, role, pbar);
+            window_role(*gw, s, role >> 1, role & 1, pbar);
             quad_barrier(qbar);
             swap_regs(gw, gl);
         }
         quad_barrier(qbar);
-    } else if (role == 2) {
+    } else if (role == 4) {
         TimingState tw, tl;   // state of gw's / gl's streams
         DemodState st0, st1;  // local memory: only the out-of-line scheduler touches them
         DemodState* stw = &st0;
@@ -403,7 +398,7 @@ demod_pipe_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         timing_finish(tw, *stw, dstate, strw, counters);
         timing_finish(tl, *stl, dstate, strl, counters);
         quad_barrier(qbar);
-    } else if (role == 3) {
+    } else if (role == 5) {
         AfcState aw, al;
         afc_init(*gw, s, aw, dstate, stream0);
         afc_init(*gl, s, al, dstate, stream1);
@@ -423,39 +418,70 @@ demod_pipe_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         if (valid0) afc_finish(a0, dstate, stream0);
         if (valid1) afc_finish(a1, dstate, stream1);
     } else {
-        StageState fw, fl;
-        PendRegs pa, pb;
+        // ---- staging warp of ONE group (role 6: the quad's first, role 7: its second).  In the group's window
+        // period it requests the next 48 samples per stream (w0/live are stable then: the timing warp is on the
+        // other group); in the group's loop period (the loads have had a whole period to land) it moves them into
+        // the transposed ring.  The rows it overwrites hold samples older than the window that ran when they were
+        // requested, and the stores are complete one barrier before the group's next window.
+        // Load layout: the 384 16-byte pieces of a round are dealt to the lanes in memory order (piece m = 32 i +
+        // lane of instruction i belongs to stream m / 12), so one instruction touches ~6 lines instead of 32; the
+        // pieces then go through the linear landing buffer (128-bit stores and loads, conflict-free at a 208-byte
+        // pitch) to the lane that owns the stream.  With one line per lane the loads took 32 wavefronts each on the
+        // LSU data pipe and delayed every other warp's shared-memory loads; per-lane bulk copies (UBLKCP) serialise
+        // at ~75 cycles per copy (both measured).
+        const bool second = role == 7;
+        GroupSmem* mine = second ? gl : gw;
+        StageState f;
+        PendRegs pend;
         const int stride = (int)sb.stride;
+        uint4 (*land)[kStagePitch] = sm.landing[quad];  // shared by the quad's two staging warps: they store in
+                                                        // alternate periods
+        const uint32_t* base = sb.iq + (long long)((second ? raw1 : raw0) - s) * sb.stride;  // the group's first stream
         quad_barrier(qbar);
-        stage_init(*gw, s, fw, pa, sb, stream0);
-        stage_init(*gl, s, fl, pa, sb, stream1);
+        stage_init(*mine, s, f, pend, sb, second ? stream1 : stream0);
         quad_barrier(qbar);
-        // one period: FIRST request the next 48 samples of gw's streams into `ld` (a whole period to land), THEN
-        // store the 48 requested last period (in `st`, for the group that is gl now).  The other order makes the
-        // visit wait a full HBM latency for loads issued just before the previous barrier.
-        int idx_a = -1, idx_b = -1;  // >= 0: the buffer holds samples [idx, idx + 48) of a stream
-#define OPVD_STAGE_PERIOD(ld, ld_idx, st, st_idx)                                              \
-        ld_idx = -1;                                                                           \
-        if (gw->any_live) { /* uniform */                                                      \
-            if (gw->live[s] && fw.fill + kStageAll <= gw->w0[s] + kRingRows) {                 \
-                if (fw.fill < stride) {                                                        \
-                    stage_load(fw.row, fw.fill, stride, ld);                                   \
-                    ld_idx = fw.fill;                                                          \
-                }                                                                              \
-                fw.fill += kStageAll;                                                          \
-            }                                                                                  \
-        }                                                                                      \
-        if (st_idx >= 0) stage_store(*gl, s, st_idx, st);                                      \
-        quad_barrier(qbar);                                                                    \
-        swap_regs(gw, gl); swap_regs(fw, fl);
+        int land_idx = -1;       // >= 0: pend holds pieces of samples [land_idx, land_idx + 48) of this lane's stream
+        bool in_flight = false;  // uniform: pend holds a round
 #pragma unroll 1
-        for (int p = 0;; p += 2) {
+        for (int p = 0;; ++p) {
             if (OPVD_PIPE_EXIT(p)) break;
-            OPVD_STAGE_PERIOD(pa, idx_a, pb, idx_b)
-            if (OPVD_PIPE_EXIT(p + 1)) break;
-            OPVD_STAGE_PERIOD(pb, idx_b, pa, idx_a)
+            if (gw == mine) {  // the group's window period: request
+                land_idx = -1;
+                if (mine->any_live) {  // uniform
+                    if (mine->live[s] && f.fill + kStageAll <= mine->w0[s] + kRingRows) {
+                        if (f.fill < stride) land_idx = f.fill;
+                        f.fill += kStageAll;
+                    }
+                    if (__any_sync(0xffffffffu, land_idx >= 0)) {
+#pragma unroll
+                        for (int i = 0; i < kStageVec; ++i) {
+                            const int m = 32 * i + s, sig = m / kStageVec, c = m - kStageVec * sig;
+                            const int ridx = __shfl_sync(0xffffffffu, land_idx, sig);
+                            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                            if (ridx >= 0 && ridx + 4 * c + 4 <= stride)
+                                v = ldg_stream(reinterpret_cast<const uint4*>(base + (long long)sig * stride + ridx) + c);
+                            pend[i] = v;
+                        }
+                        in_flight = true;
+                    }
+                }
+            } else if (in_flight) {  // the group's loop period: store
+#pragma unroll
+                for (int i = 0; i < kStageVec; ++i) {
+                    const int m = 32 * i + s, sig = m / kStageVec;
+                    land[sig][m - kStageVec * sig] = pend[i];
+                }
+                __syncwarp();
+                if (land_idx >= 0) {
+#pragma unroll
+                    for (int j = 0; j < kStageVec; ++j) pend[j] = land[s][j];
+                    stage_store(*mine, s, land_idx, pend);
+                }
+                in_flight = false;
+            }
+            quad_barrier(qbar);
+            swap_regs(gw, gl);
         }
-#undef OPVD_STAGE_PERIOD
         quad_barrier(qbar);
     }
 #undef OPVD_PIPE_EXIT
