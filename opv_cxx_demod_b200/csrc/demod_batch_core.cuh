@@ -40,6 +40,21 @@ OPVD_HD cplx horner10(const double* I, const double* Q, cplx z) {
     return g;
 }
 
+// The same block sum as two 5-sample Horner chains joined by z5 = z^5: same operation count (36), half the
+// dependent depth — for kernels where one warp has to keep the FP64 pipe busy on its own.
+OPVD_HD cplx horner10_split(const double* I, const double* Q, cplx z, cplx z5) {
+    cplx lo = {I[4], Q[4]}, hi = {I[9], Q[9]};
+#pragma unroll
+    for (int r = 3; r >= 0; --r) {
+        const double lr = fma(lo.r, z.r, fma(-lo.i, z.i, I[r]));
+        const double li = fma(lo.r, z.i, fma(lo.i, z.r, Q[r]));
+        const double hr = fma(hi.r, z.r, fma(-hi.i, z.i, I[r + 5]));
+        const double hq = fma(hi.r, z.i, fma(hi.i, z.r, Q[r + 5]));
+        lo.r = lr; lo.i = li; hi.r = hr; hi.i = hq;
+    }
+    return cfma(z5, hi, lo);
+}
+
 // one tone, one window half, from the half's three block sums A, B, C (slots 30h.., 30h+10.., 30h+20..) and
 // the three raw samples its edge terms need: e0, e1, e2 = slots 0, 10, 20 (h = 0) or 40, 50, 60 (h = 1).
 // Returns the interpolated partial gates.
@@ -88,6 +103,7 @@ OPVD_HD HalfGates batch_half_gates(const double* I, const double* Q, cplx z, cpl
 struct ToneLo {
     cplx z, q;
     double inc;
+    cplx z5;  // z^5 (horner10_split)
 };
 OPVD_HD void batch_lo(double freq_offset, ToneLo& t1, ToneLo& t2) {
     const LoSteps l = lo_steps(freq_offset);  // Taylor zeta, sincos fallback for huge -o offsets
@@ -95,6 +111,7 @@ OPVD_HD void batch_lo(double freq_offset, ToneLo& t1, ToneLo& t2) {
     cplx a = csqr(l.z1), b = csqr(l.z2);      // z^2
     cplx a4 = csqr(a), b4 = csqr(b);          // z^4
     a = cmul(a4, l.z1); b = cmul(b4, l.z2);   // z^5
+    t1.z5 = a; t2.z5 = b;
     t1.q = csqr(a); t2.q = csqr(b);           // z^10
 }
 
@@ -109,6 +126,7 @@ OPVD_HD void batch_lo_fast(double freq_offset, ToneLo& t1, ToneLo& t2, const Fas
     cplx a = csqr(t1.z), b = csqr(t2.z);      // z^2
     const cplx a4 = csqr(a), b4 = csqr(b);    // z^4
     a = cmul(a4, t1.z); b = cmul(b4, t2.z);   // z^5
+    t1.z5 = a; t2.z5 = b;
     t1.q = csqr(a); t2.q = csqr(b);           // z^10
 }
 

@@ -45,7 +45,7 @@ struct __align__(16) GroupSmem {
     uint32_t ring[kRows][kSpc];     // transposed sample ring (Q offset-binary), 40 KB
     double2 part[2][2][3][kSpc];    // [tone][half][E,O,L] interpolated partial gates
     double tg[2][7][kSpc];          // per tone: eE, eO, eL, O.r, O.i, z40.r, z40.i
-    double zq[2][4][kSpc];          // [tone][z.r, z.i, q.r, q.i]: LO steps of the group's next window
+    double zq[2][6][kSpc];          // [tone][z.r, z.i, q.r, q.i, z5.r, z5.i]: LO steps of the group's next window
     double frac[kSpc];              // interpolation fraction of the next window
     int w0[kSpc];                   // row-relative sample index of slot 0 of the next window
     int live[kSpc], first[kSpc];    // next window: stream has a symbol / it is the first of a call
@@ -136,6 +136,7 @@ __device__ __forceinline__ void window_role(GroupSmem& sm, int s, int tone, int 
     }
     const uint32_t* win = &sm.ring[w0 & (kRingRows - 1)][s];
     const cplx z = {sm.zq[tone][0][s], sm.zq[tone][1][s]}, q = {sm.zq[tone][2][s], sm.zq[tone][3][s]};
+    const cplx z5 = {sm.zq[tone][4][s], sm.zq[tone][5][s]};
     if (lv) {
         // two passes keep the register footprint small (a spill is an L2 round trip here: nearly all of L1 is
         // carved out as shared memory): blocks 0-1 of the half, then block 2
@@ -145,7 +146,7 @@ __device__ __forceinline__ void window_role(GroupSmem& sm, int s, int tone, int 
             double I[20], Q[20];
 #pragma unroll
             for (int j = 0; j < 20; ++j) unpack_ring(src[j * kSpc], I[j], Q[j]);
-            A = horner10(I, Q, z); B = horner10(I + 10, Q + 10, z);
+            A = horner10_split(I, Q, z, z5); B = horner10_split(I + 10, Q + 10, z, z5);
             s0 = {I[0], Q[0]}; s10 = {I[10], Q[10]};
         }
         {
@@ -154,7 +155,7 @@ __device__ __forceinline__ void window_role(GroupSmem& sm, int s, int tone, int 
             for (int j = 0; j < 10; ++j) unpack_ring(src[(20 + j) * kSpc], I[j], Q[j]);
             I[10] = 0.0; Q[10] = 0.0;
             if (half) unpack_ring(src[30 * kSpc], I[10], Q[10]);
-            C = horner10(I, Q, z);
+            C = horner10_split(I, Q, z, z5);
             s20 = {I[0], Q[0]}; s30 = {I[10], Q[10]};
         }
         const HalfGates g = half_gates_from_blocks(A, B, C, half ? s10 : s0, half ? s20 : s10, half ? s30 : s20, z, q, f, half);
@@ -300,6 +301,7 @@ struct AfcState {
 __device__ __forceinline__ void afc_publish(GroupSmem& sm, int s, const ToneLo& t1, const ToneLo& t2) {
     sm.zq[0][0][s] = t1.z.r; sm.zq[0][1][s] = t1.z.i; sm.zq[0][2][s] = t1.q.r; sm.zq[0][3][s] = t1.q.i;
     sm.zq[1][0][s] = t2.z.r; sm.zq[1][1][s] = t2.z.i; sm.zq[1][2][s] = t2.q.r; sm.zq[1][3][s] = t2.q.i;
+    sm.zq[0][4][s] = t1.z5.r; sm.zq[0][5][s] = t1.z5.i; sm.zq[1][4][s] = t2.z5.r; sm.zq[1][5][s] = t2.z5.i;
 }
 __device__ __forceinline__ void afc_init(GroupSmem& sm, int s, AfcState& a, const DemodState* dstate, int stream) {
     const DemodState* d = dstate + stream;
@@ -345,11 +347,13 @@ demod_pipe_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PipeSmem& sm = *reinterpret_cast<PipeSmem*>(smem_raw);
     const int s = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // Warps land on SM sub-partitions by warp id mod 4; in each quad warps 0-3 are the window workers (tone =
-    // w >> 1, half = w & 1), so every sub-partition hosts one window worker of each quad; 4 timing, 5 AFC,
-    // 6 / 7 staging of the quad's first / second group.
+    // Warps land on SM sub-partitions by warp id mod 4.  In each quad warps 0-3 are the window workers (tone =
+    // w >> 1, half = w & 1), so every sub-partition hosts one window worker of each quad.  The other four roles
+    // (4 timing, 5 AFC, 6 / 7 staging of the quad's first / second group) are rotated by two warps in quad 1, so
+    // that the two AFC warps (as much FP64 work as a window worker) sit on different sub-partitions.
     const int quad = warp / kQuadWarps;
-    const int role = warp - kQuadWarps * quad;
+    const int wq = warp - kQuadWarps * quad;
+    const int role = wq < 4 ? wq : 4 + ((wq + 2 * quad) & 3);
     const int qbar = 1 + 3 * quad, pbar = 2 + 3 * quad + ((role >> 1) & 1);
     GroupSmem* gw = &sm.g[2 * quad];  // group whose WINDOW runs in the current period (period 0: the quad's first)
     GroupSmem* gl = gw + 1;           // group whose LOOP runs in the current period
