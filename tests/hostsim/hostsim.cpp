@@ -10,6 +10,7 @@
 #include "../../opv_cxx_demod_b200/csrc/demod_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/demod_warp_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/demod_batch_core.cuh"
+#include "../../opv_cxx_demod_b200/csrc/demod_pipe_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/demod_coherent_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/est_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/track_core.cuh"
@@ -207,6 +208,64 @@ size_t hostsim_demod_batch(const int16_t* iq, size_t n, int mode, double afc_alp
         if (first) { fix1 = first_symbol_fix(win, f, r.t1.z); fix2 = first_symbol_fix(win, f, r.t2.z); }
         const ToneGates g1 = batch_finish_tone(hg[0][0], hg[0][1], r.t1, fix1);
         const ToneGates g2 = batch_finish_tone(hg[1][0], hg[1][1], r.t2, fix2);
+        const double soft = batch_symbol_serial(r, g1, g2, first, afc_alpha, g_fm);
+        st.sym_in_call++;
+        if (ns < cap) soft_out[ns] = soft;
+        ++ns;
+        st.n_sym++;
+    }
+    if (est_out) *est_out = est;
+    if (final_freq) *final_freq = r.freq_offset;
+    if (final_tfreq) *final_tfreq = r.timing_freq;
+    return ns;
+}
+
+// whole stream through the PIPELINED kernel's decomposition (demod_pipe_core.cuh): four quarter "threads" per
+// symbol (15 window slots each, both tones), one finishing thread per tone, then the serial lane.
+size_t hostsim_demod_pipe(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
+                          double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
+    std::vector<uint32_t> w(n + 64 + 64, 0xDEADBEEFu);
+    for (size_t i = 0; i < n; ++i)
+        w[64 + i] = (uint32_t)(uint16_t)iq[2 * i] | ((uint32_t)(uint16_t)iq[2 * i + 1] << 16);
+    const uint32_t* base = w.data() + 64;
+
+    DemodState st;
+    demod_state_init(st);
+    double est = 0.0;
+    if (mode == kModeBatch) {
+        est = hostsim_estimate(iq, n);
+        st.freq_offset = est;
+    } else if (have_init) {
+        st.freq_offset = init_offset;
+    } else if (n >= (size_t)kChunkSamples) {
+        est = hostsim_estimate(iq, kChunkSamples);
+        st.freq_offset = est;
+    }
+    st.flags |= kFlagEstDone;
+    BatchRegs r;
+    r.freq_offset = st.freq_offset; r.ph1 = st.ph1; r.ph2 = st.ph2; r.pos = st.pos; r.timing_freq = st.timing_freq;
+    r.p1 = st.p1; r.p2 = st.p2;
+    batch_lo(r.freq_offset, r.t1, r.t2);
+    size_t ns = 0;
+    while (demod_schedule(st, r.pos, mode, (int64_t)n, true)) {
+        const int64_t b = (int64_t)r.pos;
+        const double f = r.pos - (double)b;
+        const uint32_t* win = base + st.origin + b - kWinLead;
+        const bool first = st.sym_in_call == 0;
+        QuarterParts qp[2][4];
+        for (int q = 0; q < 4; ++q) {
+            double I[15], Q[15];
+            for (int j = 0; j < 15; ++j) unpack_iq(win[15 * q + j], I[j], Q[j]);
+            qp[0][q] = quarter_parts(I, Q, r.t1.z, r.t1.z5, q);
+            qp[1][q] = quarter_parts(I, Q, r.t2.z, r.t2.z5, q);
+        }
+        cplx edge[6];
+        const int slots[6] = {0, 10, 20, 40, 50, 60};
+        for (int e = 0; e < 6; ++e) unpack_iq(win[slots[e]], edge[e].r, edge[e].i);
+        cplx fix1 = {0.0, 0.0}, fix2 = {0.0, 0.0};
+        if (first) { fix1 = first_symbol_fix(win, f, r.t1.z); fix2 = first_symbol_fix(win, f, r.t2.z); }
+        const ToneGates g1 = finish_tone_quarters(qp[0], edge, r.t1, f, fix1);
+        const ToneGates g2 = finish_tone_quarters(qp[1], edge, r.t2, f, fix2);
         const double soft = batch_symbol_serial(r, g1, g2, first, afc_alpha, g_fm);
         st.sym_in_call++;
         if (ns < cap) soft_out[ns] = soft;
