@@ -22,7 +22,6 @@
 #include <cstdint>
 
 #include "demod_batch_core.cuh"
-#include "demod_pipe_core.cuh"
 #include "demod_warp_core.cuh"  // first_symbol_fix_w
 #include "opvd_kernels.cuh"
 
@@ -36,16 +35,15 @@ constexpr int kGroups = 2 * kQuads; // stream groups per CTA
 constexpr int kQuadWarps = 8;      // four window workers (tone x half), timing, AFC, two staging warps
 constexpr int kThreads = 32 * kQuadWarps * kQuads;
 constexpr int kRingRows = 256;      // samples per stream resident in shared memory (power of two)
-constexpr int kMirrorRows = 16;     // rows 0..15 repeated after row 255: a 16-row quarter window (and the 11 rows
-constexpr int kRows = kRingRows + kMirrorRows;  // the first-symbol fix reads) never wraps
+constexpr int kMirrorRows = 64;     // rows 0..63 are repeated after row 255 (the first 60 of them are stored):
+constexpr int kRows = kRingRows + kWin - 1;  // a 61-row window starting at row <= 255 never wraps
 constexpr int kSub = 8;             // samples per 32-byte sector (2 x LDG.128)
 constexpr int kStageVec = 12;       // uint4 per stream and visit
 constexpr int kStageAll = 4 * kStageVec;  // samples staged per stream and symbol (48)
 
 struct __align__(16) GroupSmem {
-    uint32_t ring[kRows][kSpc];     // transposed sample ring (Q offset-binary), 34 KB
-    double2 part[2][4][2][kSpc];    // [tone][quarter][P, R] partial sums (demod_pipe_core.cuh)
-    uint32_t edge[6][kSpc];         // ring words of window slots 0, 10, 20, 40, 50, 60 (interpolator edge terms)
+    uint32_t ring[kRows][kSpc];     // transposed sample ring (Q offset-binary), 40 KB
+    double2 part[2][2][3][kSpc];    // [tone][half][E,O,L] interpolated partial gates
     double tg[2][7][kSpc];          // per tone: eE, eO, eL, O.r, O.i, z40.r, z40.i
     double zq[2][6][kSpc];          // [tone][z.r, z.i, q.r, q.i, z5.r, z5.i]: LO steps of the group's next window
     double frac[kSpc];              // interpolation fraction of the next window
@@ -63,8 +61,9 @@ struct __align__(16) PipeSmem {
 };
 static_assert(sizeof(PipeSmem) <= 227 * 1024, "pipe kernel shared memory");
 
-// named barriers: 1 + 2*quad = the quad (256 threads), 2 + 2*quad = its four window workers (128 threads)
+// named barriers: 1 + 3*quad = the quad (256 threads), 2 + 3*quad + tone = the two window workers of a tone
 __device__ __forceinline__ void quad_barrier(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 constexpr uint32_t kQBias = 0x80000000u;
 // ring word (I raw, Q offset-binary) -> doubles.  I through I2F.F64.S16 (XU pipe), Q through the 2^52
@@ -114,85 +113,71 @@ __device__ __forceinline__ void stage_store(GroupSmem& sm, int s, int idx, const
         for (int j = 0; j < 8; ++j) sm.ring[row + j][s] = w[j];
         if (row < kMirrorRows) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sm.ring[kRingRows + row + j][s] = w[j];
+            for (int j = 0; j < 8; ++j)
+                if (j < 4 || row + 8 <= kRows - kRingRows) sm.ring[kRingRows + row + j][s] = w[j];  // rows 256..315
         }
     }
 }
 
-// ---- window worker w = 0..3: quarter w of the window (slots 15w .. 15w+14) for both tones; after the four
-// workers' barrier each of them finishes part of a tone (combine the quarters, interpolate): its early/late
-// energies or its on-time sum
-__device__ __forceinline__ void window_role(GroupSmem& sm, int s, int w, int wbar) {
+// ---- window worker (tone, half): 30 samples of the window for one tone; then the half-0 worker of the tone
+// combines the two halves and publishes the tone's gate energies / on-time sum
+__device__ __forceinline__ void window_role(GroupSmem& sm, int s, int tone, int half, int pbar) {
     if (!sm.any_live) {  // uniform
-        if (w == 0 && s == 0) sm.ran = 0;
+        if ((tone | half) == 0 && s == 0) sm.ran = 0;
         return;
     }
     const int lv = sm.live[s], w0 = sm.w0[s];
     const bool first = sm.first[s] != 0;
     const double f = sm.frac[s];
-    if (w == 0) {
+    if ((tone | half) == 0) {
         sm.sym_live[s] = lv;
         sm.sym_first[s] = first;
         if (s == 0) sm.ran = 1;
     }
+    const uint32_t* win = &sm.ring[w0 & (kRingRows - 1)][s];
+    const cplx z = {sm.zq[tone][0][s], sm.zq[tone][1][s]}, q = {sm.zq[tone][2][s], sm.zq[tone][3][s]};
+    const cplx z5 = {sm.zq[tone][4][s], sm.zq[tone][5][s]};
     if (lv) {
-        const uint32_t* src = &sm.ring[(w0 + 15 * w) & (kRingRows - 1)][s];  // 16 rows from here never wrap
-        uint32_t word[16];
+        // two passes keep the register footprint small (a spill is an L2 round trip here: nearly all of L1 is
+        // carved out as shared memory): blocks 0-1 of the half, then block 2
+        const uint32_t* src = win + 30 * half * kSpc;
+        cplx A, B, C, s0, s10, s20, s30;
+        {
+            double I[20], Q[20];
 #pragma unroll
-        for (int j = 0; j < 15; ++j) word[j] = src[j * kSpc];
-        word[15] = src[15 * kSpc];  // slot 60 for w = 3 (any resident row otherwise)
-        // the interpolator's edge samples travel as ring words
-        if (w == 0) { sm.edge[0][s] = word[0]; sm.edge[1][s] = word[10]; }
-        else if (w == 1) sm.edge[2][s] = word[5];
-        else if (w == 2) sm.edge[3][s] = word[10];
-        else { sm.edge[4][s] = word[5]; sm.edge[5][s] = word[15]; }
-        double I[15], Q[15];
-#pragma unroll
-        for (int j = 0; j < 15; ++j) unpack_ring(word[j], I[j], Q[j]);
-#pragma unroll
-        for (int tone = 0; tone < 2; ++tone) {
-            const cplx z = {sm.zq[tone][0][s], sm.zq[tone][1][s]}, z5 = {sm.zq[tone][4][s], sm.zq[tone][5][s]};
-            const QuarterParts p = quarter_parts(I, Q, z, z5, w);
-            sm.part[tone][w][0][s] = make_double2(p.P.r, p.P.i);
-            sm.part[tone][w][1][s] = make_double2(p.R.r, p.R.i);
+            for (int j = 0; j < 20; ++j) unpack_ring(src[j * kSpc], I[j], Q[j]);
+            A = horner10_split(I, Q, z, z5); B = horner10_split(I + 10, Q + 10, z, z5);
+            s0 = {I[0], Q[0]}; s10 = {I[10], Q[10]};
         }
+        {
+            double I[11], Q[11];  // slots 30h+20 .. 30h+29, and slot 60 for the late gate's edge term (h = 1)
+#pragma unroll
+            for (int j = 0; j < 10; ++j) unpack_ring(src[(20 + j) * kSpc], I[j], Q[j]);
+            I[10] = 0.0; Q[10] = 0.0;
+            if (half) unpack_ring(src[30 * kSpc], I[10], Q[10]);
+            C = horner10_split(I, Q, z, z5);
+            s20 = {I[0], Q[0]}; s30 = {I[10], Q[10]};
+        }
+        const HalfGates g = half_gates_from_blocks(A, B, C, half ? s10 : s0, half ? s20 : s10, half ? s30 : s20, z, q, f, half);
+        sm.part[tone][half][0][s] = make_double2(g.E.r, g.E.i);
+        sm.part[tone][half][1][s] = make_double2(g.O.r, g.O.i);
+        sm.part[tone][half][2][s] = make_double2(g.L.r, g.L.i);
     }
-    asm volatile("bar.sync %0, 128;" ::"r"(wbar) : "memory");  // the quad's four window workers
-    if (lv) {
-        // all four workers finish: worker w takes tone w >> 1; even w its early/late energies, odd w its on-time sum
-        const int tone = w >> 1;
-        QuarterParts p[4];
-        cplx edge[6];
+    pair_barrier(pbar);
+    if (lv && half == 0) {
+        HalfGates a, b;
+        double2 v;
+        v = sm.part[tone][0][0][s]; a.E = {v.x, v.y}; v = sm.part[tone][0][1][s]; a.O = {v.x, v.y};
+        v = sm.part[tone][0][2][s]; a.L = {v.x, v.y};
+        v = sm.part[tone][1][0][s]; b.E = {v.x, v.y}; v = sm.part[tone][1][1][s]; b.O = {v.x, v.y};
+        v = sm.part[tone][1][2][s]; b.L = {v.x, v.y};
         ToneLo t;
-        t.z = {sm.zq[tone][0][s], sm.zq[tone][1][s]};
-        t.q = {sm.zq[tone][2][s], sm.zq[tone][3][s]};
-        t.z5 = {sm.zq[tone][4][s], sm.zq[tone][5][s]};
-        t.inc = 0.0;
-        if ((w & 1) == 0) {
-            { const double2 a = sm.part[tone][0][0][s]; p[0].P = {a.x, a.y}; }
-            { const double2 a = sm.part[tone][1][0][s], b = sm.part[tone][1][1][s]; p[1].P = {a.x, a.y}; p[1].R = {b.x, b.y}; }
-            { const double2 a = sm.part[tone][2][0][s], b = sm.part[tone][2][1][s]; p[2].P = {a.x, a.y}; p[2].R = {b.x, b.y}; }
-            { const double2 b = sm.part[tone][3][1][s]; p[3].R = {b.x, b.y}; }
-            p[0].R = p[0].P; p[3].P = p[3].R;  // not used by the early/late gates
-            unpack_ring(sm.edge[0][s], edge[0].r, edge[0].i); unpack_ring(sm.edge[2][s], edge[2].r, edge[2].i);
-            unpack_ring(sm.edge[3][s], edge[3].r, edge[3].i); unpack_ring(sm.edge[5][s], edge[5].r, edge[5].i);
-            edge[1] = edge[0]; edge[4] = edge[0];
-            cplx fix = {0.0, 0.0};
-            if (first) fix = first_fix_cold(&sm.ring[w0 & (kRingRows - 1)][s], f, t.z);  // early-gate clamp (:237)
-            const EarlyLate g = finish_early_late(p, edge, t, f, fix);
-            sm.tg[tone][0][s] = g.eE; sm.tg[tone][2][s] = g.eL;
-        } else {
-            { const double2 b = sm.part[tone][0][1][s]; p[0].R = {b.x, b.y}; }
-            { const double2 a = sm.part[tone][1][0][s]; p[1].P = {a.x, a.y}; }
-            { const double2 b = sm.part[tone][2][1][s]; p[2].R = {b.x, b.y}; }
-            { const double2 a = sm.part[tone][3][0][s]; p[3].P = {a.x, a.y}; }
-            p[0].P = p[0].R; p[1].R = p[1].P; p[2].P = p[2].R; p[3].R = p[3].P;  // not used by the on-time gate
-            unpack_ring(sm.edge[1][s], edge[1].r, edge[1].i); unpack_ring(sm.edge[4][s], edge[4].r, edge[4].i);
-            edge[0] = edge[1]; edge[2] = edge[1]; edge[3] = edge[1]; edge[5] = edge[1];
-            const OnTimeGate g = finish_on_time(p, edge, t, f);
-            sm.tg[tone][1][s] = g.eO;
-            sm.tg[tone][3][s] = g.O.r; sm.tg[tone][4][s] = g.O.i; sm.tg[tone][5][s] = g.z40.r; sm.tg[tone][6][s] = g.z40.i;
-        }
+        t.z = z; t.q = q; t.inc = 0.0;
+        cplx fix = {0.0, 0.0};
+        if (first) fix = first_fix_cold(win, f, t.z);  // early-gate clamp (:237), once per call
+        const ToneGates g = batch_finish_tone(a, b, t, fix);
+        sm.tg[tone][0][s] = g.eE; sm.tg[tone][1][s] = g.eO; sm.tg[tone][2][s] = g.eL;
+        sm.tg[tone][3][s] = g.O.r; sm.tg[tone][4][s] = g.O.i; sm.tg[tone][5][s] = g.z40.r; sm.tg[tone][6][s] = g.z40.i;
     }
 }
 
@@ -369,7 +354,7 @@ demod_pipe_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     const int quad = warp / kQuadWarps;
     const int wq = warp - kQuadWarps * quad;
     const int role = wq < 4 ? wq : 4 + ((wq + 2 * quad) & 3);
-    const int qbar = 1 + 2 * quad, wbar = 2 + 2 * quad;
+    const int qbar = 1 + 3 * quad, pbar = 2 + 3 * quad + ((role >> 1) & 1);
     GroupSmem* gw = &sm.g[2 * quad];  // group whose WINDOW runs in the current period (period 0: the quad's first)
     GroupSmem* gl = gw + 1;           // group whose LOOP runs in the current period
     const int raw0 = (blockIdx.x * kGroups + 2 * quad) * kSpc + s, raw1 = raw0 + kSpc;
@@ -391,7 +376,7 @@ demod_pipe_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
 #pragma unroll 1
         for (int p = 0;; ++p) {
             if (OPVD_PIPE_EXIT(p)) break;
-            window_role(*gw, s, role, wbar);
+            window_role(*gw, s, role >> 1, role & 1, pbar);
             quad_barrier(qbar);
             swap_regs(gw, gl);
         }
