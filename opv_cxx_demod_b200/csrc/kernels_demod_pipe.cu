@@ -2,22 +2,23 @@
 // Same arithmetic as kernels_demod_batch.cu (demod_batch_core.cuh); different schedule.
 //
 // The batched kernel alternates a window phase and a loop phase per symbol, so at any time about half
-// of its warps wait at a barrier, and its window warps convert every sample once per tone.  Here a CTA
-// of 256 threads (one per SM) is two independent QUADS of four warps; a quad owns TWO groups of 32
-// streams and its warps are specialised:
-//   warps W0, W1  window workers: half h of the 60-sample window for BOTH tones (samples are loaded and
-//                 converted once), then — after a two-warp named barrier — W_h combines the halves of
-//                 tone h and publishes its gate energies / on-time sum;
-//   warp  T       timing chain of the group whose window finished one period earlier (soft decision,
-//                 TED, timing loop, call schedule, soft store) and that group's ring staging (128-bit
-//                 global loads of whole 32-byte sectors, issued one visit = one symbol before they are
-//                 stored into the transposed ring; 4-byte cp.async was measured at 32 shared-memory
-//                 wavefronts per instruction and made the first version LSU-bound);
-//   warp  A       AFC chain of the same group (phase detector, AFC loop, LO steps of its next symbol).
-// Period p: window(group p & 1) runs while loop(group ~p & 1) runs; one quad barrier (named, 128
-// threads) per period.  Warps land on SM sub-partitions by warp id, so quad 0 uses the role order
-// W0 W1 T A and quad 1 the order T A W0 W1: every sub-partition's FP64 pipe gets exactly one window
-// worker and one loop warp.  Lane = stream everywhere, so there is still no intra-warp exchange.
+// of its warps wait at a barrier.  Here a CTA of 512 threads (one per SM) is two independent QUADS of eight
+// warps; a quad owns TWO groups of 32 streams (lane = stream everywhere) and its warps are specialised:
+//   4 window workers (tone t, half h): 30 samples of the 60-sample window for one tone in two passes (blocks
+//                 0-1, then block 2: the register budget at 512 threads is 128), 10-sample block sums by two
+//                 5-step Horner chains joined by z^5, interpolated partial gates; after a two-warp named
+//                 barrier the half-0 worker of the tone combines the halves and publishes the tone's gate
+//                 energies / on-time sum;
+//   timing warp   timing chain of the group whose window finished one period earlier (soft decision, TED,
+//                 timing loop, call schedule, soft store);
+//   AFC warp      AFC chain of the same group (phase detector, AFC loop, LO steps z, z^5, z^10 of its next symbol);
+//   2 staging warps, one per group: request 48 samples per stream in the group's window period (coalesced:
+//                 the 16-byte pieces are dealt to the lanes in memory order), move them through a landing
+//                 buffer into the transposed shared-memory ring in the group's loop period.
+// Period p: window(group p & 1) runs while loop(group ~p & 1) runs; one quad barrier (named, 256 threads) per
+// period.  Warps land on SM sub-partitions by warp id: every sub-partition hosts one window worker of each
+// quad, and the other roles are rotated between the quads.  DESIGN.md section 3.2.1 lists the measurements
+// behind each of these choices.
 #include <cuda_runtime.h>
 #include <cstdint>
 
