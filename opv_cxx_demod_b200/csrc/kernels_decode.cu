@@ -6,10 +6,13 @@
 //
 // Viterbi layout: 64 states, 2 per lane.  Lane j holds the path metrics of states j and j+32
 // (the two predecessors of states 2j and 2j+1), packed as 2 x int16 in one register, so the
-// add-compare-select butterfly is lane-local: two 32-bit adds form all four candidates, one DPX
-// __vibmin_s16x2 does both compare-selects and returns the two decision predicates with the
-// reference's tie rule (a <= b keeps predecessor p0, :829).  The new metrics are redistributed with
-// two warp shuffles + one byte-permute.  Metrics are bounded by 2144*7 = 15,008, so int16 holds
+// add-compare-select butterfly is lane-local: the two packed branch metrics of the step come from a
+// 64-entry table (indexed by the step's two 3-bit symbols, XORed per lane with the lane's expected
+// coded bits), two 32-bit adds form all four candidates, one packed signed 16-bit minimum does both
+// compare-selects, and the two decisions are the sign bits of one guarded packed subtraction, which
+// gives the reference's tie rule (a <= b keeps predecessor p0, :829).  The new metrics are
+// redistributed with two warp shuffles + two byte-permutes.  13 instructions per trellis step (the
+// kernel is issue-bound on the integer pipe).  Metrics are bounded by 2144*7 = 15,008, so int16 holds
 // them; the reference's INT_MAX "unreachable" marker (:805,:826) is replaced by 16,384, which can
 // never win against a reachable path and never reaches the final traceback.
 // Decisions (64 bits/step) live in shared memory; traceback, byte packing and the derandomiser XOR
@@ -45,9 +48,23 @@ constexpr int kDecWarps = 4;
 constexpr int kDecWords = kFrameBits / 16;                 // 67 decision words per lane
 constexpr int kDecBytesPerWarp = kDecWords * 32 * 4;       // 8576 B, aliased as 1072 doubles for the scale sum
 constexpr int kQBytesPerWarp = kEncodedBits;               // deinterleaved 3-bit symbols, one byte each
-constexpr int kOutBytesPerWarp = 144;
+constexpr int kOutBytesPerWarp = 16;                      // (the 134 output bytes alias the symbol area, dead by then)
 constexpr int kDecSmemPerWarp = kDecBytesPerWarp + kQBytesPerWarp + kOutBytesPerWarp;  // 10,864 B
+constexpr int kBmTableBytes = 64 * 8;                      // per CTA: packed branch metrics by (u1, u2)
 constexpr int kUnreachable = 16384;
+
+// Branch-metric table, shared by the CTA: entry (u1 | u2 << 3) holds, for a butterfly whose predecessor
+// p0 expects coded bits whose costs are u1 and u2 (:823-824 with e1/e2 folded in by the caller's XOR),
+//   x = A0 | (14 - A0) << 16,  A0 = u1 + u2         p0 = state j,    input 0 | input 1 (both coded bits flip)
+//   y = B0 | (14 - B0) << 16,  B0 = u1 + (u2 ^ 7)   p1 = state j+32 (G2 taps register bit 5, G1 does not)
+__device__ __forceinline__ void build_bm_table(uint2* tbl) {
+    for (int e = threadIdx.x; e < 64; e += blockDim.x) {
+        const uint32_t u1 = e & 7, u2 = e >> 3;
+        const uint32_t A0 = u1 + u2, B0 = u1 + (u2 ^ 7u);
+        tbl[e] = make_uint2(A0 * 0xFFFF0001u + 0x000E0000u, B0 * 0xFFFF0001u + 0x000E0000u);
+    }
+    __syncthreads();
+}
 
 // inverse of deinterleave_addr: deint[i] = q[deinterleave_addr(i)]  =>  q index j feeds deint index inv(j)
 __device__ __forceinline__ int deinterleave_inv(int j) {
@@ -55,13 +72,13 @@ __device__ __forceinline__ int deinterleave_inv(int j) {
     return (pos % 67) * 32 + pos / 67;
 }
 
-__device__ __forceinline__ void decode_one(const double* __restrict__ soft, unsigned char* wsm, uint8_t* out_frame,
-                                           int32_t* out_metric, unsigned long long* counters) {
+__device__ __forceinline__ void decode_one(const double* __restrict__ soft, unsigned char* wsm, const uint2* bm_tbl,
+                                           uint8_t* out_frame, int32_t* out_metric, unsigned long long* counters) {
     const int lane = threadIdx.x & 31;
     double* dsum = reinterpret_cast<double*>(wsm);
     uint32_t* dec = reinterpret_cast<uint32_t*>(wsm);
     uint8_t* q = wsm + kDecBytesPerWarp;
-    uint8_t* outb = q + kQBytesPerWarp;
+    uint8_t* outb = q;  // written after the forward pass has consumed the symbols
 
     // ---- scale = mean |soft| with the reference's sequential summation order (:856-858)
     double scale = 0.0;
@@ -91,38 +108,44 @@ __device__ __forceinline__ void decode_one(const double* __restrict__ soft, unsi
     }
     __syncwarp();
 
+    // ---- per-step table offsets: (sg1 | sg2 << 3) * 8, in place over the symbol pairs
+    uint16_t* qoff = reinterpret_cast<uint16_t*>(q);
+    for (int t = lane; t < kFrameBits; t += 32) {
+        const uint32_t sg = qoff[t];  // sg1 | sg2 << 8
+        qoff[t] = (uint16_t)(((sg & 7u) | ((sg >> 5) & 0x38u)) << 3);
+    }
+    __syncwarp();
+
     // ---- forward pass
     const uint32_t k1 = __popc(lane & 0x4F) & 1 ? 7u : 0u;  // parity(j & G1) -> expected coded bit 1
     const uint32_t k2 = __popc(lane & 0x6D) & 1 ? 7u : 0u;
-    const uint32_t psel = (lane & 1) ? 0x7632u : 0x5410u;
-    // ab = metric[state lane] | metric[state lane+32] << 16
-    uint32_t ab = (lane == 0 ? 0u : (uint32_t)kUnreachable) | ((uint32_t)kUnreachable << 16);
+    const uint32_t xmask = (k1 | (k2 << 3)) << 3;            // table offset XOR of this lane
+    const uint32_t sel = (lane & 1) ? 0x3232u : 0x1010u;     // which half of the fetched pairs this lane needs
+    const int src0 = lane >> 1, src1 = 16 + (lane >> 1);
+    const unsigned char* tblb = reinterpret_cast<const unsigned char*>(bm_tbl);
+    // aa = a | a << 16, bb = b | b << 16 with a = metric[state lane], b = metric[state lane + 32]
+    uint32_t aa = lane == 0 ? 0u : (uint32_t)kUnreachable * 0x00010001u;
+    uint32_t bb = (uint32_t)kUnreachable * 0x00010001u;
     uint32_t dreg = 0;
     uint32_t newp = 0;
-    const uint16_t* q2 = reinterpret_cast<const uint16_t*>(q);
+#pragma unroll 16
     for (int t = 0; t < kFrameBits; ++t) {
-        const uint32_t sg = q2[t];  // sg1 | sg2 << 8, lane-uniform
-        const uint32_t u1 = (sg & 0xFFu) ^ k1;   // cost of coded bit e1 on predecessor lane (in=0)
-        const uint32_t u2 = (sg >> 8) ^ k2;
-        const uint32_t A0 = u1 + u2;             // p0=state j,    in=0
-        const uint32_t B0 = u1 + (u2 ^ 7u);      // p1=state j+32, in=0 (G2 taps bit 5, G1 does not)
-        // in=1 flips both coded bits: A1 = 14 - A0, B1 = 14 - B0
-        const uint32_t bmA = A0 * 0xFFFF0001u + 0x000E0000u;  // A0 | (14-A0) << 16
-        const uint32_t bmB = B0 * 0xFFFF0001u + 0x000E0000u;
-        const uint32_t aa = __byte_perm(ab, 0, 0x1010);  // a | a << 16
-        const uint32_t bb = __byte_perm(ab, 0, 0x3232);  // b | b << 16
-        bool p_hi, p_lo;
-        newp = __vibmin_s16x2(aa + bmA, bb + bmB, &p_hi, &p_lo);  // lo: state 2j, hi: state 2j+1
-        const uint32_t d = (p_lo ? 0u : 1u) | (p_hi ? 0u : 2u);    // decision 1 = came from p1
-        dreg |= d << (2 * (t & 15));
+        const uint32_t off = qoff[t] ^ xmask;  // lane-uniform load
+        const uint2 bm = *reinterpret_cast<const uint2*>(tblb + off);
+        const uint32_t X = aa + bm.x, Y = bb + bm.y;  // lo halves: state 2j (input 0), hi halves: state 2j+1
+        newp = __vmins2(X, Y);
+        // per half Y + 0x8000 - X stays inside 16 bits (metrics < 2^15): bit 15 set <=> X <= Y <=> predecessor p0
+        const uint32_t D = (Y + 0x80008000u) - X;
+        dreg = (dreg >> 1) | (~D & 0x80008000u);       // decision 1 = came from p1; after 16 steps bit k / 16 + k
         if ((t & 15) == 15) {
             dec[(t >> 4) * 32 + lane] = dreg;
             dreg = 0;
         }
         // redistribute: lane j needs new metrics of states j (lane j>>1) and j+32 (lane 16 + j>>1)
-        const uint32_t v0 = __shfl_sync(0xffffffffu, newp, lane >> 1);
-        const uint32_t v1 = __shfl_sync(0xffffffffu, newp, 16 + (lane >> 1));
-        ab = __byte_perm(v0, v1, psel);
+        const uint32_t v0 = __shfl_sync(0xffffffffu, newp, src0);
+        const uint32_t v1 = __shfl_sync(0xffffffffu, newp, src1);
+        aa = __byte_perm(v0, 0, sel);
+        bb = __byte_perm(v1, 0, sel);
     }
     __syncwarp();
 
@@ -132,19 +155,25 @@ __device__ __forceinline__ void decode_one(const double* __restrict__ soft, unsi
     key = __reduce_min_sync(0xffffffffu, key);
 
     // ---- traceback + pack + derandomise (:839-843, :878-895)
+    // The state register is kept left-aligned in S (state = S >> 26) and doubles as the shift register of the
+    // decisions: a step is S = (d : S) >> 1 (one funnel shift), the bit the reference emits at that step
+    // (state & 1, :840) is bit 26 before the shift, so after the 8 steps of an output byte the byte is
+    // (S >> 18) & 0xFF with the first-emitted bit in bit 0 (:878-884).  7 instructions per step on lane 0.
     if (lane == 0) {
-        int s = (int)(key & 0xFFu);
-        uint32_t acc = 0;
-        for (int t = kFrameBits - 1; t >= 0; --t) {
-            const int jb = (kFrameBits - 1 - t) & 7;
-            acc |= (uint32_t)(s & 1) << jb;
-            const uint32_t w = dec[(t >> 4) * 32 + (s >> 1)];
-            const uint32_t d = (w >> (2 * (t & 15) + (s & 1))) & 1u;
-            s = (s >> 1) | (int)(d << 5);
-            if (jb == 7) {
-                const int i = (kFrameBits - 1 - t) >> 3;
-                outb[i] = (uint8_t)(acc ^ c_lfsr[i]);
-                acc = 0;
+        uint32_t S = (key & 0xFFu) << 26;
+        const unsigned char* decb = reinterpret_cast<const unsigned char*>(dec);
+#pragma unroll 1
+        for (int wd = kDecWords - 1; wd >= 0; --wd) {
+            const unsigned char* wb = decb + wd * 128;  // decision words of steps 16 wd .. 16 wd + 15, one per lane
+#pragma unroll
+            for (int k = 15; k >= 0; --k) {             // step t = 16 wd + k
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(wb + ((S >> 25) & 0x7Cu));  // lane state >> 1
+                const uint32_t hi = w >> (((S >> 22) & 16u) | (uint32_t)k);  // bit k (even state) or 16 + k (odd)
+                S = __funnelshift_r(S, hi, 1);                               // state = state >> 1 | d << 5 (:841-842)
+                if (k == 8 || k == 0) {
+                    const int i = 2 * (kDecWords - 1 - wd) + (k == 0 ? 1 : 0);
+                    outb[i] = (uint8_t)((S >> 18) ^ c_lfsr[i]);
+                }
             }
         }
         const int metric = (int)(key >> 8);
@@ -165,12 +194,14 @@ decode_tasks_kernel(SoftBuffers so, const FrameTask* __restrict__ tasks, const i
     const int warp = threadIdx.x >> 5;
     int n = *n_tasks_dev;
     if (n > max_tasks) n = max_tasks;
-    unsigned char* wsm = dsm + (size_t)warp * kDecSmemPerWarp;
+    uint2* bm_tbl = reinterpret_cast<uint2*>(dsm);
+    build_bm_table(bm_tbl);
+    unsigned char* wsm = dsm + kBmTableBytes + (size_t)warp * kDecSmemPerWarp;
     for (int task = blockIdx.x * kDecWarps + warp; task < n; task += gridDim.x * kDecWarps) {
         const FrameTask ft = tasks[task];
         const double* soft = so.soft + (long long)ft.stream * so.stride - so.base + ft.payload_start;
         const long long o = (long long)ft.stream * max_frames + (ft.slot % max_frames);
-        decode_one(soft, wsm, frames + o * kFrameBytes, metrics + o, counters);
+        decode_one(soft, wsm, bm_tbl, frames + o * kFrameBytes, metrics + o, counters);
         __syncwarp();
     }
 }
@@ -180,9 +211,11 @@ decode_payloads_kernel(const double* __restrict__ payloads, int n, uint8_t* __re
                        int32_t* __restrict__ metrics, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char dsm[];
     const int warp = threadIdx.x >> 5;
-    unsigned char* wsm = dsm + (size_t)warp * kDecSmemPerWarp;
+    uint2* bm_tbl = reinterpret_cast<uint2*>(dsm);
+    build_bm_table(bm_tbl);
+    unsigned char* wsm = dsm + kBmTableBytes + (size_t)warp * kDecSmemPerWarp;
     for (int task = blockIdx.x * kDecWarps + warp; task < n; task += gridDim.x * kDecWarps) {
-        decode_one(payloads + (long long)task * kEncodedBits, wsm, frames + (long long)task * kFrameBytes,
+        decode_one(payloads + (long long)task * kEncodedBits, wsm, bm_tbl, frames + (long long)task * kFrameBytes,
                    metrics + task, counters);
         __syncwarp();
     }
@@ -203,7 +236,7 @@ void launch_decode(const SoftBuffers& so, const FrameTask* tasks, const int32_t*
                    cudaStream_t st) {
     // n_tasks_host is an upper bound used only to size the grid; the kernel reads the exact count on device
     if (n_tasks_host <= 0) return;
-    const size_t smem = (size_t)kDecWarps * kDecSmemPerWarp;
+    const size_t smem = (size_t)kBmTableBytes + (size_t)kDecWarps * kDecSmemPerWarp;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(decode_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -217,7 +250,7 @@ void launch_decode(const SoftBuffers& so, const FrameTask* tasks, const int32_t*
 void launch_decode_payloads(const double* payloads, int n, uint8_t* frames, int32_t* metrics,
                             unsigned long long* counters, cudaStream_t st) {
     if (n <= 0) return;
-    const size_t smem = (size_t)kDecWarps * kDecSmemPerWarp;
+    const size_t smem = (size_t)kBmTableBytes + (size_t)kDecWarps * kDecSmemPerWarp;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(decode_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
