@@ -54,7 +54,8 @@ typedef struct opvd_config {
     int32_t max_frames;        /* per-stream frame ring (frames decoded but not yet polled); 0 = derived */
     int32_t lanes_per_stream;  /* demodulator kernel variant: 0 = chosen from n_streams; 1, 2, 4 = lanes per stream
                                   of the lane kernels; 32 = one warp per stream (small banks, lowest per-symbol
-                                  latency); 64 = batched, 32 streams per 128-thread CTA (large banks) */
+                                  latency); 64 = batched, 32 streams per 128-thread CTA (large banks); 128 = pipelined
+                                  batched, 128 streams per 512-thread CTA (experimental) */
     int32_t coherent;          /* -c: CoherentMSKDemodulator (:365-572) instead of MSKDemodulatorAFC; honoured in batch
                                   mode only, like the reference (the streaming branch returns first, :995-1125) */
     int32_t reserved0;

@@ -13,6 +13,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libopvd.so")
 CLI_PATH = os.path.join(HERE, "bin", "opv-demod")
+BANK_CLI_PATH = os.path.join(os.path.dirname(CLI_PATH), "opv-demod-bank")
 
 FRAME_BYTES = 134
 FRAME_SYMBOLS = 2168

@@ -305,13 +305,15 @@ static cudaError_t launch_t(const StreamBuffers& sb, const SoftBuffers& so, Demo
 }
 
 int demod_auto_lanes(int n_streams) {
-    // Small banks are bound by the per-symbol latency of the serial recurrence: one warp per stream, as
-    // long as every stream's warp is resident at once (12 warps per SM at the kernel's register count).
-    // Larger banks: the batched kernel (32 streams per CTA), which spends ~5x fewer instructions per
-    // stream and symbol.  The lane kernels (1, 2, 4) stay selectable for comparison.
+    // Small banks are bound by the per-symbol latency of the serial recurrence: one warp per stream (12 resident
+    // warps per SM at the kernel's register count; it peaks at 82 Gsample/s with 1,776 streams).  Larger banks: the
+    // batched kernel (32 streams per CTA), which spends ~5x fewer instructions per stream and symbol and scales with
+    // the stream count (108 Gsample/s at 4,096 streams, 320 at 18,944).  Measured crossover (profiles/README.md,
+    // round-1 "e" sweep): ~17 streams per SM.  The lane kernels (1, 2, 4) and the pipelined kernel (128) stay
+    // selectable for comparison.
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if ((long long)n_streams <= 12ll * sms) return 32;
+    if ((long long)n_streams <= 17ll * sms) return 32;
     return 64;
 }
 

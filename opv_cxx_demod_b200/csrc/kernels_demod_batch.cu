@@ -87,11 +87,23 @@ __device__ __forceinline__ void stage_store(BatchSmem& sm, int s, int idx, const
 }
 // 24 samples of a row starting at idx (multiple of 8); rows are 16-byte aligned and a multiple of 4
 // samples long, so only the last chunk of a row can be partial
-__device__ __forceinline__ void stage_load(const uint32_t* row, int idx, int stride, uint4 (&v)[6]) {
+__device__ __forceinline__ void ldg256_stream(const uint32_t* p, uint4& a, uint4& b) {  // read-once, 32-byte aligned
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+// `wide`: rows are 32-byte aligned (row pointer and stride), so a whole sector travels in one 256-bit load: every
+// lane reads its own line, and the LSU data pipe spends one wavefront per line and instruction, not per byte
+__device__ __forceinline__ void stage_load(const uint32_t* row, int idx, int stride, bool wide, uint4 (&v)[6]) {
     const uint4* p = reinterpret_cast<const uint4*>(row + idx);
     if (idx + kStage <= stride) {
+        if (wide) {
 #pragma unroll
-        for (int j = 0; j < 6; ++j) v[j] = __ldg(p + j);
+            for (int j = 0; j < 3; ++j) ldg256_stream(row + idx + 8 * j, v[2 * j], v[2 * j + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) v[j] = __ldg(p + j);
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < 6; ++j) v[j] = (idx + 4 * j + 4 <= stride) ? __ldg(p + j) : make_uint4(0u, 0u, 0u, 0u);
@@ -175,6 +187,7 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
     const long long row0 = sb.row_base;
     const uint32_t* __restrict__ row = sb.iq + (long long)stream * sb.stride;  // row[r] = absolute sample row0 + r
     const int stride_i = (int)sb.stride;
+    const bool wide = ((reinterpret_cast<uintptr_t>(sb.iq) | (uintptr_t)(sb.stride * 4)) & 31u) == 0;
 
     // ---- loop-phase state.  warp 0: timing chain + call schedule; warp 1: AFC chain
     DemodState st;                      // warp 0 (lives in local memory: only the scheduler touches it)
@@ -230,7 +243,7 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
                 const int idx = fill + kStage * (k - 2);
                 if (idx < stride_i) {
                     uint4 v[6];
-                    stage_load(row, idx, stride_i, v);
+                    stage_load(row, idx, stride_i, wide, v);
                     stage_store(sm, s, idx, v);
                 }
                 fill += kStageAll;
@@ -322,7 +335,7 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
             if (lv && fill + kStageAll <= w0 + kRingRows) {
                 const int idx = fill + kStage * (k - 2);
                 if (idx < stride_i) {
-                    stage_load(row, idx, stride_i, pend);
+                    stage_load(row, idx, stride_i, wide, pend);
                     pend_idx = idx;
                 }
                 fill += kStageAll;

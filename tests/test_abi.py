@@ -59,6 +59,24 @@ def test_no_cpu_fallback(built):
     assert p.returncode == 2 and b"no CPU fallback" in p.stderr and p.stdout == b""
 
 
+def test_bank_cli_no_cpu_fallback_and_help(built, tmp_path):
+    """the multi-stream front-end (opv-demod-bank) obeys the same rules: help on -h, exit 2 without a device"""
+    import torch
+
+    assert os.path.exists(built.BANK_CLI_PATH)
+    p = subprocess.run([built.BANK_CLI_PATH, "-h"], capture_output=True)
+    assert p.returncode == 0 and b"FILE" in p.stderr and b"-s" in p.stderr
+    p = subprocess.run([built.BANK_CLI_PATH], capture_output=True)
+    assert p.returncode == 2 and b"no input files" in p.stderr
+    if torch.cuda.is_available():
+        return
+    f = tmp_path / "a.iq"
+    f.write_bytes(b"\0" * 4000)
+    p = subprocess.run([built.BANK_CLI_PATH, "-s", "-q", str(f)], capture_output=True)
+    assert p.returncode == 2 and b"no CPU fallback" in p.stderr
+    assert not os.path.exists(str(f) + ".frames") or os.path.getsize(str(f) + ".frames") == 0
+
+
 def test_cli_help_contract(built):
     p = subprocess.run([built.CLI_PATH, "-h"], capture_output=True)
     assert p.returncode == 0 and b"-s" in p.stderr and b"-r" in p.stderr and b"-o <hz>" in p.stderr

@@ -200,6 +200,33 @@ def test_cli_dropin_vs_reference_process(name, flags, pkg, cases, ora):
         assert keep(rerr) == keep(err)
 
 
+@pytest.mark.parametrize("flags", [[], ["-s"]])
+def test_bank_cli_matches_per_stream_reference(flags, pkg, cases, ora, tmp_path):
+    """opv-demod-bank: N capture files in one GPU bank -> per stream exactly the bytes `opv-demod [-s] -r -q < FILE`
+    writes (golden sha256 of the unmodified reference's stdout), and the bank-level exit code."""
+    names = ["clean5", "awgn8", "cfo_p1200_delay", "dropout_long", "tiny", "empty", "short_lt_chunk", "clean12_call"]
+    files = []
+    for k, name in enumerate(names):
+        f = tmp_path / f"{k:02d}_{name}.iq"
+        np.ascontiguousarray(cases[name]).tofile(f)
+        files.append(str(f))
+    out = tmp_path / "out"
+    out.mkdir()
+    p = subprocess.run([pkg.BANK_CLI_PATH, *flags, "-d", str(out), *files], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode("utf8", "replace")[-600:]
+    mode = "stream" if "-s" in flags else "batch"
+    total = 0
+    for k, name in enumerate(names):
+        got = open(out / f"{k:02d}_{name}.iq.frames", "rb").read()
+        g = GOLD[f"{name}/{mode}"]
+        assert hashlib.sha256(got).hexdigest() == g["frames_sha256"], name
+        total += len(got) // 134
+    assert f"Summary: {len(names)} streams, {total} frames".encode() in p.stderr
+    # a bank in which no stream decodes anything exits 1, like the reference process (:1124)
+    p = subprocess.run([pkg.BANK_CLI_PATH, *flags, "-q", "-d", str(out), files[4], files[5]], capture_output=True)
+    assert p.returncode == 1 and p.stderr == b""
+
+
 def test_synth_bank_matches_tx_restatement(pkg, ora):
     """The device generator without impairments reproduces opv-mod's waveform (apart from rare +/-1 LSB
     truncation flips caused by opv-mod's accumulated phase rounding) and decodes to its BERT payloads."""
