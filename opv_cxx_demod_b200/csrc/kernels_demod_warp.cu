@@ -7,10 +7,13 @@
 // the gate sums are formed by three shuffle-down steps, the uniform loop arithmetic (soft decision,
 // TED, timing loop) runs redundantly on all lanes, the AFC atan2 runs on the on-time gate lanes.
 //
-// Samples reach shared memory through an 8-slot ring of 64-sample (256-byte) TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx) issued by lane 0 six slots (~9 symbols) ahead of the window,
-// so HBM is read exactly once in 256-byte bursts and its latency is hidden even with one resident
-// warp.  Lanes address the ring modulo its size, so no mirror copy is needed.
+// Samples reach shared memory through an 8-slot ring of 64-sample (256-byte) slots filled by 16-byte
+// cp.async copies (lanes 0-15, one fully coalesced 256-byte burst per slot) issued seven slots (~11
+// symbols) ahead of the window, so HBM is read exactly once, no register (and no register scoreboard)
+// is tied to a load in flight, and its latency is hidden even with one resident warp.  The first
+// version used cp.async.bulk + mbarriers issued by lane 0: its bookkeeping (uniform-datapath address
+// arithmetic, expect_tx, try_wait, two loops per symbol) was 95 of the 319 instructions and ~400 of the
+// ~1,340 cycles of a symbol (profiles/ncu_demod_warp_r01_d.txt and the source-level capture).
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -22,29 +25,12 @@ namespace opvd {
 namespace {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(mbar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-        "l"(src), "r"(bytes), "r"(mbar)
-        : "memory");
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 constexpr int kSlotShift = 6;
 constexpr int kSlotSamples = 1 << kSlotShift;  // 64 samples = 256 B per bulk copy
@@ -70,46 +56,50 @@ struct WarpCtx {
     bool prev_zero;      // prev is exactly zero (signed-zero corner of the AFC phase detector)
     double freq_offset, pos, timing_freq, ph_own, afc_alpha;
     const uint32_t* ring;
-    uint32_t ring_s, mbar_s;
+    uint32_t ring_s;
     const uint32_t* row;
     int stride_i, avail_rel, origin_rel;
-    int first_s, issued_s, ready_s;  // ring bookkeeping in samples relative to the row (multiples of 64)
+    int issued_s;        // samples [.., issued_s) of the row have been requested (multiple of 64); < 0: ring not primed
     int lane, lane_slot, tone_base;
     double* soft_ptr;    // where the next soft symbol goes (lane 0 stores)
 
-    __device__ __forceinline__ void issue_slot() {  // TMA bulk copy of the next 64-sample slot (lane 0)
-        if (lane == 0) {
-            const int p = (issued_s >> kSlotShift) & (kNumSlots - 1);
-            const int left = stride_i - issued_s;
-            const uint32_t bytes = left >= kSlotSamples ? (uint32_t)kSlotBytes : (uint32_t)(left * 4);
-            const uint32_t mb = mbar_s + 8 * p;
-            mbar_expect_tx(mb, p == 0 ? 2 * bytes : bytes);
-            tma_bulk_g2s(ring_s + p * kSlotBytes, row + issued_s, bytes, mb);
-            if (p == 0) tma_bulk_g2s(ring_s + kNumSlots * kSlotBytes, row + issued_s, bytes, mb);
+    // request the next 64-sample slot: lanes 0-15 copy 16 bytes each (slot 0 of the ring also feeds the mirror
+    // behind the ring's end, so a window never wraps)
+    __device__ __forceinline__ void issue_slot() {
+        const int p = (issued_s >> kSlotShift) & (kNumSlots - 1);
+        const int off = issued_s + 4 * lane;
+        if (lane < 16 && off + 4 <= stride_i) {  // rows are a multiple of 4 samples long
+            cp_async16(ring_s + p * kSlotBytes + 16 * lane, row + off);
+            if (p == 0) cp_async16(ring_s + kNumSlots * kSlotBytes + 16 * lane, row + off);
         }
         issued_s += kSlotSamples;
     }
-    __device__ __forceinline__ void wait_slot() {
-        const uint32_t mb = mbar_s + 8 * ((ready_s >> kSlotShift) & (kNumSlots - 1));
-        const uint32_t parity = (uint32_t)(((ready_s - first_s) >> (kSlotShift + 3)) & 1);
-        while (!mbar_try_wait(mb, parity)) {}
-        ready_s += kSlotSamples;
-    }
 
-    // keep 7 slots in flight ahead of the window starting at row index w0 (slot s recycles the ring
-    // position of slot s-8), and have everything up to w0 + kLookahead landed: that covers this
-    // symbol's window AND the next one's (it starts at most 42 samples later), so the next window can
-    // be loaded mid-symbol without another check.
-    static constexpr int kLookahead = (kWin - 1) + 44;
+    // Once per symbol: keep 7 slots requested ahead of the window starting at row index w0 (slot s recycles the
+    // ring position of slot s-8, whose samples are all older than w0), and have every copy group older than four
+    // symbols landed.  A slot is requested when issued_s <= w0 + 448, i.e. at least 448 - 64 - 105 = 279 samples
+    // (6.5 symbols) before the window of the NEXT symbol (it ends at most at w0 + 105) can touch it, so the next
+    // window can be loaded mid-symbol without another check.  One slot per symbol is enough: a symbol consumes at
+    // most 43 samples.
     __device__ __forceinline__ void ring_maintain(int w0) {
-        while (w0 + (kNumSlots - 1) * kSlotSamples >= issued_s && issued_s < avail_rel) {
+        if (w0 + (kNumSlots - 1) * kSlotSamples >= issued_s && issued_s < avail_rel) {
             __syncwarp();  // every lane is done with the slot about to be recycled
             issue_slot();
             // the absolute LO phase is only read in the signed-zero corner: advance it unwrapped in
             // the symbol loop and wrap it here, every ~1.6 symbols (|ph| stays < 10 rad)
             ph_own = warp_wrap_phase(ph_own, K);
         }
-        while (w0 + kLookahead >= ready_s && ready_s < issued_s) wait_slot();
+        cp_async_commit();
+        cp_async_wait<4>();
+        __syncwarp();  // the copies of lanes 0-15 are visible to every lane
+    }
+    // first symbol of a launch: fill the ring up to seven slots ahead of the window and wait for all of it
+    __device__ __forceinline__ void ring_prime(int w0) {
+        issued_s = w0 < 0 ? 0 : (w0 & ~(kSlotSamples - 1));
+        while (w0 + (kNumSlots - 1) * kSlotSamples >= issued_s && issued_s < avail_rel) issue_slot();
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
     }
     __device__ __forceinline__ void load_window(int b, uint32_t (&s5)[5]) const {
         const uint32_t* src = ring + (((origin_rel + b - kWinLead) & kRingMask) + lane_slot);
@@ -180,7 +170,6 @@ __global__ void __launch_bounds__(32)
 demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
                   int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
     __shared__ __align__(128) uint32_t ring_sm[kRingWords];
-    __shared__ __align__(8) unsigned long long mbar_sm[kNumSlots];
     const int lane = threadIdx.x;
     const int stream = blockIdx.x;
 
@@ -189,14 +178,6 @@ demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     c.lane = lane;
     c.ring = ring_sm;
     c.ring_s = smem_u32(ring_sm);
-    c.mbar_s = smem_u32(mbar_sm);
-    if (lane == 0) {
-#pragma unroll
-        for (int p = 0; p < kNumSlots; ++p) mbar_init(c.mbar_s + 8 * p, 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
 
     DemodState st = dstate[stream];
     const long long avail = sb.avail[stream];
@@ -219,8 +200,7 @@ demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     c.pos = st.pos;
     c.timing_freq = st.timing_freq;
     c.ph_own = c.wl.tone ? st.ph2 : st.ph1;  // this lane's tone's absolute LO phase
-    c.first_s = -1;
-    c.issued_s = c.ready_s = 0;
+    c.issued_s = -1;
 
     const long long n_sym0 = st.n_sym, origin0 = st.origin;
     for (;;) {
@@ -231,13 +211,9 @@ demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         const int call_len_i = (int)st.call_len;
         const double call_len_d = (double)st.call_len;
         int b = __double2int_rz(c.pos);  // pos >= 0: truncation == floor (:125)
-        if (c.first_s < 0) {  // first symbol of this launch: prime the ring
-            const int w0 = c.origin_rel + b - kWinLead;
-            c.first_s = w0 < 0 ? 0 : (w0 & ~(kSlotSamples - 1));
-            c.issued_s = c.ready_s = c.first_s;
-        }
         uint32_t s5[5];
-        c.ring_maintain(c.origin_rel + b - kWinLead);
+        if (c.issued_s < 0) c.ring_prime(c.origin_rel + b - kWinLead);  // first symbol of this launch
+        else c.ring_maintain(c.origin_rel + b - kWinLead);
         c.load_window(b, s5);
         if (st.sym_in_call == 0) {
             b = c.symbol<true>(b, s5);

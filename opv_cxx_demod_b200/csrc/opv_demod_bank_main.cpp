@@ -11,7 +11,8 @@
 // FILE: raw interleaved int16 LE I/Q (the reference's stdin bytes).  Output: <outdir>/<basename>.frames
 // (default outdir: next to the input), concatenated 134-byte frames in stream order.  -s: streaming
 // semantics (86,720-sample calls with carry, :1012-1113), fed in time tiles so that host memory stays
-// bounded; without -s: batch semantics (whole capture in one call, :1127-1216).  Exit code 0 iff at least one
+// bounded and frames leave as they complete; without -s: batch semantics (whole capture in one call,
+// :1127-1216).  GPU memory holds the captures (4 bytes per sample and stream).  Exit code 0 iff at least one
 // frame was decoded in any stream (the per-process rule of :1124 applied to the bank).
 #include <algorithm>
 #include <cstdint>
@@ -131,9 +132,12 @@ int main(int argc, char* argv[]) {
     cfg.device = device;
     cfg.coherent = coherent ? 1 : 0;
     cfg.pll_bw_hz = pll_bw;
-    // stream mode: tiles of 8 calls per stream and run; batch mode: the whole capture is one call (:1164-1166)
+    // stream mode: fed in tiles of 8 calls per stream and run (bounded host memory, frames leave as they complete);
+    // batch mode: the whole capture is one call (:1164-1166).  The captures stay resident on the GPU in both
+    // modes: the library drops consumed samples from the front of ALL rows at once, and a bank of unequal files
+    // always holds a short stream that still needs its first sample at EOF.
     const int64_t tile = streaming ? 8 * (int64_t)OPVD_CHUNK_SAMPLES : std::max<int64_t>(max_n, 64);
-    cfg.max_samples = streaming ? 2 * tile : tile;
+    cfg.max_samples = std::max<int64_t>(max_n, 64);
     cfg.max_frames = (int32_t)(tile / OPVD_CHUNK_SAMPLES + 8);
     opvd_handle* h = nullptr;
     int rc = opvd_create(&cfg, &h);

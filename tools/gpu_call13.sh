@@ -2,7 +2,7 @@
 # Round-1 "d" evidence: GPU tests, smoke, bench (both arms), ncu launch list, ncu full captures of the three demod kernels.
 set -x
 mkdir -p gpurun_out
-TAG=r01_d
+TAG=r01_e
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv
 nproc; free -g | head -2
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
@@ -14,10 +14,10 @@ tail -1 gpurun_out/bench_$TAG.json | cut -c1-3000; tail -3 gpurun_out/bench_$TAG
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu_$TAG.log 2>&1
 grep -c . gpurun_out/launches_$TAG.csv
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:demod_warp_kernel -c 1 -f -o gpurun_out/prof_warp_$TAG \
-    python tools/probe.py --streams 1024 --frames 4 --reps 1 > gpurun_out/ncu_warp_$TAG.log 2>&1
+
+
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:decode_tasks_kernel -c 1 -f -o gpurun_out/prof_decode_$TAG \
     python tools/probe.py --streams 18944 --frames 2 --reps 1 --lanes 64 > gpurun_out/ncu_decode_$TAG.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:est_kernel -c 1 -f -o gpurun_out/prof_est_$TAG \
-    python tools/probe.py --streams 18944 --frames 2 --reps 1 --lanes 64 > gpurun_out/ncu_est_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:demod_batch_kernel -c 1 -f -o gpurun_out/prof_batch_$TAG \
+    python tools/probe.py --streams 18944 --frames 2 --reps 1 --lanes 64 > gpurun_out/ncu_batch_$TAG.log 2>&1
 ls -la gpurun_out
