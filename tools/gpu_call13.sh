@@ -21,3 +21,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:deco
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:demod_batch_kernel -c 1 -f -o gpurun_out/prof_batch_$TAG \
     python tools/probe.py --streams 18944 --frames 2 --reps 1 --lanes 64 > gpurun_out/ncu_batch_$TAG.log 2>&1
 ls -la gpurun_out
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:demod_warp_kernel -c 1 -f -o gpurun_out/prof_warp_$TAG \
+    python tools/probe.py --streams 1024 --frames 4 --reps 1 > gpurun_out/ncu_warp_$TAG.log 2>&1
