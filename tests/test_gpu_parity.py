@@ -297,6 +297,49 @@ def test_resident_bank_properties_and_reference_spotcheck(pkg, ora):
     bank.close()
 
 
+@pytest.mark.parametrize("shape", ["configs2_4096_cfo_delay", "configs4_16384_bank"])
+def test_baseline_config_shapes_at_scale(shape, pkg, ora):
+    """BASELINE.json configs[2] (4,096 streams, CFO up to +/-2 kHz and fractional timing offset: AFC + early-late STR)
+    and configs[4] (a 16,384-stream channel bank) at their full stream counts and a short duration, through the
+    automatic kernel selection (the batched kernel): size-independent properties on every stream, and frames, soft
+    symbols and sync events of a sample of streams against the oracle on the same bytes."""
+    import torch
+
+    if shape == "configs2_4096_cfo_delay":
+        S, n_frames, kw, picks = 4096, 3, dict(ebn0_lo_db=8.0, ebn0_hi_db=16.0, cfo_max_hz=2000.0, frac_delay=True,
+                                               max_lead=30000), [0, 1, 511, 1024, 2047, 3000, 4095]
+    else:
+        S, n_frames, kw, picks = 16384, 2, dict(ebn0_lo_db=2.0, ebn0_hi_db=10.0, max_lead=4000), [0, 777, 8191, 8192, 16383]
+    n = n_frames * 86720 + kw["max_lead"] + 4000
+    stride = (n + 63) // 64 * 64
+    buf = torch.zeros((S, stride), dtype=torch.int32, device="cuda")
+    sp = pkg.make_synth(S, n_frames, stride, n, seed=11, **kw)
+    pkg.synth_bank(buf.data_ptr(), sp)
+    bank = pkg.DemodBank(S, streaming=True)
+    assert bank.demod_variant() == "demod_batch_kernel"
+    bank.attach_device_iq(buf.data_ptr(), stride, n, keepalive=buf)
+    bank.run(final=True)
+    fr = bank.poll_frames()
+    c = bank.counters()
+    assert c["samples"] == S * n
+    assert c["frames_decoded"] == fr.data.shape[0] <= S * n_frames
+    assert c["frames_ready"] == c["frames_decoded"] + c["frames_dropped"]
+    assert c["acs"] == c["frames_decoded"] * 1072 * 64
+    for s in picks:
+        host = buf[s, :n].cpu().numpy().view(np.int16).reshape(n, 2)
+        ref = ora.run(host, True)
+        assert np.array_equal(fr.of_stream(s), ref.frames), (shape, s)
+        assert _soft_err(bank.get_soft(s), ref.soft) < SOFT_TOL
+        assert [(t, i, c2) for (t, i, c2, _, _) in bank.poll_events(s)] == [(t, i, c2) for (t, i, c2, _, _) in ref.events]
+    bank.bert_check(sp)
+    c = bank.counters()
+    assert c["frames_compared"] == c["frames_decoded"]
+    if shape == "configs2_4096_cfo_delay":  # high SNR: the AFC and the timing loop must pull every stream in
+        assert c["frames_decoded"] >= 0.9 * S * (n_frames - 1)
+        assert c["bit_errors"] <= 1e-3 * c["frames_compared"] * 1072
+    bank.close()
+
+
 COHERENT_HORIZON = 2000  # symbols over which the chaotic Costas/AFC trajectory is pinned (see tests/test_hostsim.py)
 
 
