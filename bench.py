@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--seconds", type=float, default=10.0, help="capture length per stream")
     ap.add_argument("--lanes", type=int, default=0, help="GPU lanes per stream (0 = automatic)")
     ap.add_argument("--e2e-seconds", type=float, default=0.52, help="capture length per stream for the e2e leg")
+    ap.add_argument("--e2e-tiles", type=int, default=8, help="time tiles per e2e step (H2D of a tile overlaps the kernels of the previous one)")
     ap.add_argument("--bank-streams", type=int, default=0,
                     help="streams per GPU of the channel-bank leg (0 = 4 CTAs x 32 streams per SM, 18,944 on a B200)")
     ap.add_argument("--bank-frames", type=int, default=14, help="frames per stream of the channel-bank leg")
@@ -382,10 +383,16 @@ def main():
         ebank = pkg.DemodBank(S, streaming=True, device=local_rank, max_samples=n_e, lanes_per_stream=args.lanes)
         d2h = 0
 
+        # the capture crosses PCIe in time tiles: the library copies on its own stream, so tile t+1 is in flight
+        # while the kernels of tile t run (stream mode is invariant to how the input is cut, tests/test_gpu_parity.py)
+        tiles = max(1, min(args.e2e_tiles, nf_e))
+        cuts = [n_e * t // tiles // 64 * 64 for t in range(tiles)] + [n_e]
+
         def e2e_step():
             ebank.reset()
-            ebank.push_iq_host_ptr(host.data_ptr(), n_e, n_e)
-            ebank.run(final=True, sync=False)
+            for t in range(tiles):
+                ebank.push_iq_host_ptr(host.data_ptr() + 4 * cuts[t], cuts[t + 1] - cuts[t], n_e)
+                ebank.run(final=(t == tiles - 1), sync=False)
             fr = ebank.poll_frames()
             return fr
 
@@ -401,7 +408,8 @@ def main():
         e_s = reduce_max_ms(e_s, dev)
         e_val = S * world * n_e * args.steps / e_s / 1e6
         e2e = {"value": round(e_val, 2), "unit": UNIT, "h2d_bytes_per_step": int(S * n_e * 4), "d2h_bytes_per_step": d2h,
-               "sample": f"{S} streams x {nf_e} frames ({n_e} samples) per rank per step from pinned host memory",
+               "sample": f"{S} streams x {nf_e} frames ({n_e} samples) per rank per step from pinned host memory, "
+                         f"pushed and run in {tiles} time tiles",
                "frames_per_step": int(fr.data.shape[0])}
         ebank.close()
         del host

@@ -23,6 +23,11 @@ struct opvd_handle {
     int dev = 0;
     int S = 0;
     cudaStream_t st = nullptr;
+    // host->device copies of opvd_push_iq* run on their own stream, so that the samples of the next time tile cross
+    // PCIe while the kernels of the previous opvd_run are still working; opvd_run waits for them on the device
+    cudaStream_t st_copy = nullptr;
+    cudaEvent_t ev_copy = nullptr;
+    bool copy_pending = false;
     std::string cuda_err;
 
     // input
@@ -135,6 +140,7 @@ int ensure_output_buffers(opvd_handle* h, int64_t sample_capacity) {
 
 // stream-mode housekeeping for unbounded input: drop consumed samples / soft symbols from the front
 int compact(opvd_handle* h) {
+    CK(cudaStreamSynchronize(h->st_copy));  // rows are about to move: no push may still be writing into them
     CK(cudaStreamSynchronize(h->st));
     std::vector<DemodState> ds(h->S);
     CK(cudaMemcpy(ds.data(), h->d_dstate, sizeof(DemodState) * h->S, cudaMemcpyDeviceToHost));
@@ -236,6 +242,8 @@ int opvd_create(const opvd_config* cfg, opvd_handle** out) {
     cudaGetDevice(&h->dev);
     auto fail = [&](int code) { opvd_destroy(h); return code; };
     if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) return fail(OPVD_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking) != cudaSuccess) return fail(OPVD_ERR_CUDA);
+    if (cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming) != cudaSuccess) return fail(OPVD_ERR_CUDA);
     for (auto& e : h->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return fail(OPVD_ERR_CUDA);
     upload_constants();
@@ -267,12 +275,15 @@ int opvd_create(const opvd_config* cfg, opvd_handle** out) {
 int opvd_destroy(opvd_handle* h) {
     if (!h) return OPVD_OK;
     cudaSetDevice(h->dev);
+    if (h->st_copy) cudaStreamSynchronize(h->st_copy);
     if (h->st) cudaStreamSynchronize(h->st);
     cudaFree(h->d_iq_owned); cudaFree(h->d_avail); cudaFree(h->d_dstate); cudaFree(h->d_tstate); cudaFree(h->d_est);
     cudaFree(h->d_soft); cudaFree(h->d_frec); cudaFree(h->d_frames); cudaFree(h->d_metrics); cudaFree(h->d_events);
     cudaFree(h->d_nevents); cudaFree(h->d_tasks); cudaFree(h->d_ntasks); cudaFree(h->d_counters);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+    if (h->st_copy) cudaStreamDestroy(h->st_copy);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
     return OPVD_OK;
@@ -281,7 +292,9 @@ int opvd_destroy(opvd_handle* h) {
 int opvd_reset(opvd_handle* h) {
     if (!h) return OPVD_ERR_ARG;
     CK(cudaSetDevice(h->dev));
+    CK(cudaStreamSynchronize(h->st_copy));
     CK(cudaStreamSynchronize(h->st));
+    h->copy_pending = false;
     const int have_init = (h->cfg.mode == OPVD_MODE_STREAM && h->cfg.have_init_offset) ? 1 : 0;
     init_state_kernel<<<(h->S + 127) / 128, 128, 0, h->st>>>(h->d_dstate, h->d_tstate, h->d_est, h->S, have_init,
                                                             h->cfg.init_offset_hz);
@@ -328,12 +341,16 @@ static int push_common(opvd_handle* h, int32_t first, int32_t count, const int16
     if (uniform) {
         CK(cudaMemcpy2DAsync(h->d_iq_owned + (size_t)first * h->stride + (h->h_avail[first] - h->row_base),
                              (size_t)h->stride * 4, iq, (size_t)host_stride * 4, (size_t)n * 4, (size_t)count,
-                             cudaMemcpyHostToDevice, h->st));
+                             cudaMemcpyHostToDevice, h->st_copy));
     } else {
         for (int s = first; s < first + count; ++s)
             CK(cudaMemcpyAsync(h->d_iq_owned + (size_t)s * h->stride + (h->h_avail[s] - h->row_base),
-                               iq + (size_t)(s - first) * host_stride * 2, (size_t)n * 4, cudaMemcpyHostToDevice, h->st));
+                               iq + (size_t)(s - first) * host_stride * 2, (size_t)n * 4, cudaMemcpyHostToDevice, h->st_copy));
     }
+    // the samples land in rows beyond what any enqueued kernel reads (they only append), so nothing on h->st has
+    // to be waited for; the next opvd_run waits for this event before its kernels
+    CK(cudaEventRecord(h->ev_copy, h->st_copy));
+    h->copy_pending = true;
     for (int s = first; s < first + count; ++s) h->h_avail[s] += n;
     h->avail_dirty = true;
     return OPVD_OK;
@@ -390,6 +407,10 @@ int opvd_run(opvd_handle* h, int final_flag) {
         CK(cudaStreamSynchronize(h->st));  // h_avail is pageable; keep it stable until the copy has landed
         h->avail_dirty = false;
     }
+    if (h->copy_pending) {  // pushed samples must have landed before the kernels read them (device-side wait)
+        CK(cudaStreamWaitEvent(h->st, h->ev_copy, 0));
+        h->copy_pending = false;
+    }
     StreamBuffers sb{h->d_iq, h->stride, h->d_avail, h->row_base};
     SoftBuffers so{h->d_soft, h->soft_stride, h->soft_base};
     CK(cudaMemsetAsync(h->d_ntasks, 0, sizeof(int32_t), h->st));
@@ -421,6 +442,7 @@ int opvd_run(opvd_handle* h, int final_flag) {
 int opvd_sync(opvd_handle* h) {
     if (!h) return OPVD_ERR_ARG;
     CK(cudaSetDevice(h->dev));
+    CK(cudaStreamSynchronize(h->st_copy));
     CK(cudaStreamSynchronize(h->st));
     CK(cudaGetLastError());
     return OPVD_OK;
