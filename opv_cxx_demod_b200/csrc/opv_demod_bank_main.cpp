@@ -6,7 +6,12 @@
 // ONE bank on one GPU.  Per stream the result is byte-for-byte what `opv-demod [-s] -r -q < FILE` writes to
 // stdout (tests/test_gpu_parity.py::test_bank_cli_matches_per_stream_reference).
 //
-//   opv-demod-bank [-s] [-c] [-a alpha] [-p hz] [-o hz] [--device n] [-d outdir] [-l listfile] [-q] FILE...
+//   opv-demod-bank [-s] [-c] [-a alpha] [-p hz] [-o hz] [--device n] [-d outdir] [-l listfile] [-u port] [-q] FILE...
+//
+// -u PORT: the RX egress of `opv-modem -R` for a whole bank (src/opv-modem.cpp:673-838: every 134-byte frame
+// read from the demodulator is one UDP datagram to 127.0.0.1:<response port>, :782): stream k's frames are
+// also sent, one datagram each, to 127.0.0.1:(PORT + k), so one Interlocutor per receiver can listen on its
+// own port.
 //
 // FILE: raw interleaved int16 LE I/Q (the reference's stdin bytes).  Output: <outdir>/<basename>.frames
 // (default outdir: next to the input), concatenated 134-byte frames in stream order.  -s: streaming
@@ -14,6 +19,11 @@
 // bounded and frames leave as they complete; without -s: batch semantics (whole capture in one call,
 // :1127-1216).  GPU memory holds the captures (4 bytes per sample and stream).  Exit code 0 iff at least one
 // frame was decoded in any stream (the per-process rule of :1124 applied to the bank).
+#include <arpa/inet.h>
+#include <netinet/in.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -48,7 +58,10 @@ std::string base_name(const std::string& p) {
 
 const char* state_name(int s) { return s == 0 ? "HUNTING" : (s == 1 ? "VERIFYING" : "LOCKED"); }
 
-// frames decoded so far -> the streams' output files, in (stream, frame) order as the library returns them
+int g_udp_sock = -1, g_udp_port = 0;
+
+// frames decoded so far -> the streams' output files (and UDP ports), in (stream, frame) order as the library
+// returns them
 int drain(opvd_handle* h, std::vector<Input>& in) {
     std::vector<uint8_t> fr(256 * OPVD_FRAME_BYTES);
     std::vector<opvd_frame_info> fi(256);
@@ -58,6 +71,13 @@ int drain(opvd_handle* h, std::vector<Input>& in) {
         for (int k = 0; k < n; ++k) {
             Input& s = in[(size_t)fi[k].stream];
             fwrite(&fr[(size_t)k * OPVD_FRAME_BYTES], 1, OPVD_FRAME_BYTES, s.out);
+            if (g_udp_sock >= 0) {  // one frame = one datagram (src/opv-modem.cpp:782)
+                sockaddr_in dst{};
+                dst.sin_family = AF_INET;
+                dst.sin_port = htons((uint16_t)(g_udp_port + fi[k].stream));
+                dst.sin_addr.s_addr = inet_addr("127.0.0.1");
+                sendto(g_udp_sock, &fr[(size_t)k * OPVD_FRAME_BYTES], OPVD_FRAME_BYTES, 0, (sockaddr*)&dst, sizeof(dst));
+            }
             ++s.decoded;
             if (fi[k].metric == 0) ++s.perfect;
         }
@@ -82,15 +102,17 @@ int main(int argc, char* argv[]) {
         else if (!strcmp(argv[i], "-o") && i + 1 < argc) { init_offset = atof(argv[++i]); have_init = true; }
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-d") && i + 1 < argc) outdir = argv[++i];
+        else if (!strcmp(argv[i], "-u") && i + 1 < argc) g_udp_port = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-l") && i + 1 < argc) {
             std::ifstream lf(argv[++i]);
             for (std::string line; std::getline(lf, line);)
                 if (!line.empty()) files.push_back(line);
         } else if (!strcmp(argv[i], "-h")) {
             fprintf(stderr,
-                    "Usage: %s [-s] [-c] [-a bw] [-p hz] [-o hz] [--device n] [-d outdir] [-l listfile] [-q] FILE...\n"
+                    "Usage: %s [-s] [-c] [-a bw] [-p hz] [-o hz] [--device n] [-d outdir] [-l listfile] [-u port] [-q] FILE...\n"
                     "  every FILE (int16 LE I/Q) is one stream of the bank; frames go to <outdir>/<basename>.frames\n"
-                    "  -s/-c/-a/-p/-o as in opv-demod; all streams share them\n",
+                    "  -s/-c/-a/-p/-o as in opv-demod; all streams share them\n"
+                    "  -u port: also send stream k's frames as UDP datagrams to 127.0.0.1:(port + k), like opv-modem -R\n",
                     argv[0]);
             return 0;
         } else files.push_back(argv[i]);
@@ -98,6 +120,12 @@ int main(int argc, char* argv[]) {
     if (files.empty()) {
         fprintf(stderr, "opv-demod-bank: no input files (-h for help)\n");
         return 2;
+    }
+    if (g_udp_port > 0) {
+        if (g_udp_port + (long)files.size() > 65536 || (g_udp_sock = socket(AF_INET, SOCK_DGRAM, 0)) < 0) {
+            fprintf(stderr, "opv-demod-bank: cannot open the UDP egress at port %d\n", g_udp_port);
+            return 2;
+        }
     }
 
     std::vector<Input> in(files.size());
@@ -179,5 +207,6 @@ int main(int argc, char* argv[]) {
         fprintf(stderr, "Summary: %zu streams, %d frames (%d perfect, %d errors)\n", in.size(), total, total_perfect,
                 total - total_perfect);
     opvd_destroy(h);
+    if (g_udp_sock >= 0) close(g_udp_sock);
     return total > 0 ? 0 : 1;
 }

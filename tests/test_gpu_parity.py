@@ -227,6 +227,51 @@ def test_bank_cli_matches_per_stream_reference(flags, pkg, cases, ora, tmp_path)
     assert p.returncode == 1 and p.stderr == b""
 
 
+def test_bank_cli_udp_egress(pkg, cases, tmp_path):
+    """opv-demod-bank -u PORT: stream k's frames leave as 134-byte UDP datagrams to 127.0.0.1:(PORT + k), the egress of
+    `opv-modem -R` (src/opv-modem.cpp:782) for a whole bank; payloads and order equal the frame files."""
+    import socket
+
+    names = ["clean5", "awgn8", "empty"]
+    socks, base = [], None
+    for attempt in range(20):  # find three consecutive free UDP ports
+        base = 40000 + 37 * attempt + os.getpid() % 1000
+        try:
+            socks = []
+            for k in range(len(names)):
+                sk = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+                sk.bind(("127.0.0.1", base + k))
+                sk.settimeout(2.0)
+                socks.append(sk)
+            break
+        except OSError:
+            for sk in socks:
+                sk.close()
+            socks = []
+    assert socks, "no free UDP ports"
+    files = []
+    for k, name in enumerate(names):
+        f = tmp_path / f"{k}_{name}.iq"
+        np.ascontiguousarray(cases[name]).tofile(f)
+        files.append(str(f))
+    p = subprocess.run([pkg.BANK_CLI_PATH, "-s", "-q", "-u", str(base), "-d", str(tmp_path), *files], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode("utf8", "replace")[-400:]
+    for k, name in enumerate(names):
+        want = open(tmp_path / f"{k}_{name}.iq.frames", "rb").read()
+        assert hashlib.sha256(want).hexdigest() == GOLD[f"{name}/stream"]["frames_sha256"]
+        got = b""
+        for _ in range(len(want) // 134):
+            d, _addr = socks[k].recvfrom(2048)
+            assert len(d) == 134
+            got += d
+        assert got == want
+        socks[k].settimeout(0.2)
+        with pytest.raises(socket.timeout):
+            socks[k].recvfrom(2048)  # nothing beyond the stream's frames
+    for sk in socks:
+        sk.close()
+
+
 def test_synth_bank_matches_tx_restatement(pkg, ora):
     """The device generator without impairments reproduces opv-mod's waveform (apart from rare +/-1 LSB
     truncation flips caused by opv-mod's accumulated phase rounding) and decodes to its BERT payloads."""
