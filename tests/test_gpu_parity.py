@@ -386,6 +386,79 @@ def test_baseline_config_shapes_at_scale(shape, pkg, ora):
     bank.close()
 
 
+def test_baseline_config3_long_captures_random_starts_and_dropouts(pkg, ora):
+    """BASELINE.json configs[3] in shape (long-capture sync search: random frame starts, dropouts shorter and longer
+    than the 5-miss flywheel limit, :60), scaled to 24 streams x 30 frames so that the oracle can check EVERY stream:
+    frames, sync events with their symbol indices, and soft symbols, in both modes, through the batched kernel."""
+    from tools import captures as cap
+
+    rng = np.random.default_rng(2026)
+    base = cap.clean_bert(30)
+    caps = []
+    for k in range(24):
+        drops = []
+        for _ in range(int(rng.integers(1, 4))):
+            start = int(rng.integers(3, 26)) * 86720 + int(rng.integers(0, 86720))
+            length = int(rng.choice([20000, 86720, 3 * 86720, 6 * 86720 + 4000]))  # < 1 frame ... > 5 frames
+            drops.append((start, length))
+        caps.append(cap.impair(base, 500 + k, ebn0_db=float(rng.uniform(5.0, 12.0)), cfo_hz=float(rng.uniform(-300, 300)),
+                               frac_delay=float(rng.uniform(0, 1)), lead_gap=int(rng.integers(0, 86720)), dropouts=drops,
+                               tail_gap=4000))
+    for streaming in (True, False):
+        bank = _run_bank(pkg, caps, streaming, lanes_per_stream=64)
+        fr = bank.poll_frames()
+        lost = 0
+        for s, c in enumerate(caps):
+            ref = ora.run(c, streaming)
+            assert np.array_equal(fr.of_stream(s), ref.frames), (s, streaming)
+            ev = [(t, i, c2) for (t, i, c2, _, _) in bank.poll_events(s)]
+            assert ev == [(t, i, c2) for (t, i, c2, _, _) in ref.events], (s, streaming)
+            assert _soft_err(bank.get_soft(s), ref.soft) < SOFT_TOL
+            lost += sum(1 for (t, _, _) in ev if t == 5)  # LOCKED -> HUNTING
+        assert lost >= 8, "the long dropouts must exercise the miss limit and re-acquisition"
+        bank.close()
+
+
+def test_abi_error_behaviour(pkg):
+    """Negative return codes, never exceptions or silent success: argument, capacity, state and
+    alignment errors through the C ABI on a live device."""
+    import ctypes as C
+
+    import torch
+
+    from opv_cxx_demod_b200 import capi
+
+    L = capi.lib()
+    h = C.c_void_p()
+    cfg = capi.Config(0, 1, 0.001, 0, -1, 0.0, 1024, 0, 0, 0, 0, 0, 50.0)
+    assert L.opvd_create(C.byref(cfg), C.byref(h)) == -1                      # n_streams <= 0: OPVD_ERR_ARG
+    cfg = capi.Config(2, 7, 0.001, 0, -1, 0.0, 1024, 0, 0, 0, 0, 0, 50.0)
+    assert L.opvd_create(C.byref(cfg), C.byref(h)) == -1                      # unknown mode
+    cfg = capi.Config(2, 0, 0.001, 0, -1, 0.0, 4096, 0, 0, 0, 0, 0, 50.0)      # batch mode, 4,096-sample rows
+    assert L.opvd_create(C.byref(cfg), C.byref(h)) == 0
+    iq = np.zeros((5000, 2), np.int16)
+    assert L.opvd_push_iq(h, 5, iq.ctypes.data_as(C.c_void_p), 100) == -1      # stream out of range
+    assert L.opvd_push_iq(h, 0, iq.ctypes.data_as(C.c_void_p), 4000) == 0
+    assert L.opvd_push_iq(h, 0, iq.ctypes.data_as(C.c_void_p), 4000) == -3     # OPVD_ERR_CAPACITY (batch rows do not compact)
+    dbuf = torch.zeros(2 * 4096 + 8, dtype=torch.int32, device="cuda")
+    assert L.opvd_attach_device_iq(h, C.c_void_p(dbuf.data_ptr()), 4096, None, 4096) == -4   # owns its input: OPVD_ERR_STATE
+    assert L.opvd_run(h, 1) == 0
+    assert L.opvd_push_iq(h, 1, iq.ctypes.data_as(C.c_void_p), 10) == -4       # after the final run: OPVD_ERR_STATE
+    assert L.opvd_poll_frames(h, 4, None, None) in (0, -1)                     # nothing decoded / no buffer
+    assert L.opvd_destroy(h) == 0
+    cfg = capi.Config(2, 0, 0.001, 0, -1, 0.0, 0, 0, 0, 0, 0, 0, 50.0)         # attach-only handle
+    assert L.opvd_create(C.byref(cfg), C.byref(h)) == 0
+    assert L.opvd_run(h, 1) == -4                                              # no input attached yet
+    assert L.opvd_attach_device_iq(h, C.c_void_p(dbuf.data_ptr() + 4), 4096, None, 4096) == -5   # OPVD_ERR_ALIGN
+    assert L.opvd_attach_device_iq(h, C.c_void_p(dbuf.data_ptr()), 4095, None, 4095) == -5       # stride % 4 != 0
+    assert L.opvd_attach_device_iq(h, C.c_void_p(dbuf.data_ptr()), 4096, None, 5000) == -1       # n > stride
+    assert L.opvd_attach_device_iq(h, C.c_void_p(dbuf.data_ptr()), 4096, None, 4096) == 0
+    assert L.opvd_push_iq(h, 0, iq.ctypes.data_as(C.c_void_p), 10) == -4       # attached captures cannot be pushed to
+    assert L.opvd_run(h, 1) == 0 and L.opvd_sync(h) == 0
+    assert L.opvd_destroy(h) == 0
+    assert L.opvd_strerror(-3).decode() and L.opvd_strerror(-5).decode()
+
+
 COHERENT_HORIZON = 2000  # symbols over which the chaotic Costas/AFC trajectory is pinned (see tests/test_hostsim.py)
 
 
