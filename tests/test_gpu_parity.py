@@ -459,6 +459,31 @@ def test_abi_error_behaviour(pkg):
     assert L.opvd_strerror(-3).decode() and L.opvd_strerror(-5).decode()
 
 
+@pytest.mark.parametrize("lanes", [32, 64, 128])
+def test_attached_rows_16_byte_aligned_only(lanes, pkg, ora):
+    """opvd_attach_device_iq promises 16-byte row alignment only (stride % 4 == 0): rows whose stride is 4 (mod 8)
+    samples are not 32-byte aligned, so the 256-bit staging loads must fall back to 128-bit ones."""
+    import torch
+
+    S, n_frames = 40, 2
+    n = n_frames * 86720 + 6000
+    stride = (n + 7) // 8 * 8 + 4
+    assert stride % 8 == 4
+    flat = torch.zeros(S * stride + 16, dtype=torch.int32, device="cuda")
+    sp = pkg.make_synth(S, n_frames, stride, n, seed=9, ebn0_lo_db=6.0, ebn0_hi_db=12.0, max_lead=3000)
+    pkg.synth_bank(flat.data_ptr(), sp)
+    bank = pkg.DemodBank(S, streaming=True, lanes_per_stream=lanes)
+    bank.attach_device_iq(flat.data_ptr(), stride, n, keepalive=flat)
+    bank.run(final=True)
+    fr = bank.poll_frames()
+    host = flat[: S * stride].cpu().numpy().view(np.int16).reshape(S, stride, 2)[:, :n]
+    for s in (0, 1, 17, 39):
+        ref = ora.run(host[s], True)
+        assert np.array_equal(fr.of_stream(s), ref.frames), (lanes, s)
+        assert _soft_err(bank.get_soft(s), ref.soft) < SOFT_TOL
+    bank.close()
+
+
 COHERENT_HORIZON = 2000  # symbols over which the chaotic Costas/AFC trajectory is pinned (see tests/test_hostsim.py)
 
 
