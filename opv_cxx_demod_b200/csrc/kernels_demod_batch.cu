@@ -23,8 +23,10 @@
 // reads bank s whatever its stream's window position is (per-stream rings laid out stream-major
 // give 3-4-way bank conflicts on every load because the window offsets of the 32 streams are
 // unrelated).  Rows 0..63 are mirrored behind row 255: a 61-row window never wraps.  Warps 2-3 fill
-// it with 128-bit global loads (each thread 96 contiguous bytes of its stream per symbol, issued one
-// full symbol before they are stored), so HBM is read exactly once, in whole 32-byte sectors.
+// it in the loop phase with 256-bit global loads (each thread 96 contiguous bytes of its stream per
+// symbol, L2-prefetched at the top of the symbol and stored in the same loop phase: loads carried over
+// the window phase stalled these warps on their shared register scoreboards), so HBM is read exactly
+// once, in whole 32-byte sectors.
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -252,8 +254,6 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
     }
     __syncthreads();  // ring primed
 
-    uint4 pend[6];  // warps 2-3: 24 samples requested during the previous symbol, stored during this one
-    int pend_idx = -1;
     const int tone = k >> 1, half = k & 1;
 
     int par = 0;  // symbol parity: which half of zq holds the current symbol's LO steps
@@ -263,6 +263,15 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
         const int w0 = sm.w0[s];
         const bool first = sm.first[s] != 0;
         const double frac = sm.frac[s];
+        // staging warps: pull the 96 bytes they will load in this symbol's loop phase into L2 now (no register and no
+        // scoreboard is tied to a prefetch): the loop-phase loads then cost an L2 hit instead of an HBM round trip
+        if (k >= 2 && lv && fill + kStageAll <= w0 + kRingRows) {
+            const int idx = fill + kStage * (k - 2);
+            if (idx + kStage <= stride_i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + idx + 8 * j));
+            }
+        }
         // ---- window phase (all four warps)
         if (lv) {
             const uint32_t* src = &sm.ring[(w0 & (kRingRows - 1)) + 30 * half][s];
@@ -328,15 +337,18 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
                 }
             }
         } else {
-            // ---- staging (warps 2-3): store the 24 samples requested one symbol ago (their rows hold samples
-            // older than any live window), then request the next ones; the loads have a whole symbol to land
-            if (pend_idx >= 0) stage_store(sm, s, pend_idx, pend);
-            pend_idx = -1;
+            // ---- staging (warps 2-3): request the next 24 samples per stream and store them in the SAME loop phase (their
+            // rows hold samples older than the window that has just been read).  The loads are not carried over the
+            // window phase: a warp with global loads in flight shares its register scoreboards with them, and the
+            // staging warps used to stall at the top of the window phase until HBM answered (8 % of all warp samples,
+            // `@!P0 BRA` long_scoreboard in the source-level profile), holding the whole CTA at the next barrier.  Here
+            // they wait while the timing and AFC warps run their chains, which take longer than an HBM round trip.
             if (lv && fill + kStageAll <= w0 + kRingRows) {
                 const int idx = fill + kStage * (k - 2);
                 if (idx < stride_i) {
+                    uint4 pend[6];
                     stage_load(row, idx, stride_i, wide, pend);
-                    pend_idx = idx;
+                    stage_store(sm, s, idx, pend);
                 }
                 fill += kStageAll;
             }
