@@ -309,11 +309,11 @@ int demod_auto_lanes(int n_streams) {
     // warps per SM at the kernel's register count; it peaks at 82 Gsample/s with 1,776 streams).  Larger banks: the
     // batched kernel (32 streams per CTA), which spends ~5x fewer instructions per stream and symbol and scales with
     // the stream count (108 Gsample/s at 4,096 streams, 320 at 18,944).  Measured crossover (profiles/README.md,
-    // round-1 "e" sweep): ~17 streams per SM.  The lane kernels (1, 2, 4) and the pipelined kernel (128) stay
+    // round-1 "f" sweep): ~16 streams per SM.  The lane kernels (1, 2, 4) and the pipelined kernel (128) stay
     // selectable for comparison.
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if ((long long)n_streams <= 17ll * sms) return 32;
+    if ((long long)n_streams <= 16ll * sms) return 32;
     return 64;
 }
 

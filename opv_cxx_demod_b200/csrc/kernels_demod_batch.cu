@@ -190,6 +190,7 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
     const uint32_t* __restrict__ row = sb.iq + (long long)stream * sb.stride;  // row[r] = absolute sample row0 + r
     const int stride_i = (int)sb.stride;
     const bool wide = ((reinterpret_cast<uintptr_t>(sb.iq) | (uintptr_t)(sb.stride * 4)) & 31u) == 0;
+    const bool prefetch = (long long)n_streams * sb.stride * 4 <= (48ll << 30);
 
     // ---- loop-phase state.  warp 0: timing chain + call schedule; warp 1: AFC chain
     DemodState st;                      // warp 0 (lives in local memory: only the scheduler touches it)
@@ -264,8 +265,12 @@ demod_batch_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
         const bool first = sm.first[s] != 0;
         const double frac = sm.frac[s];
         // staging warps: pull the 96 bytes they will load in this symbol's loop phase into L2 now (no register and no
-        // scoreboard is tied to a prefetch): the loop-phase loads then cost an L2 hit instead of an HBM round trip
-        if (k >= 2 && lv && fill + kStageAll <= w0 + kRingRows) {
+        // scoreboard is tied to a prefetch): the loop-phase loads then cost an L2 hit instead of an HBM round trip.
+        // Only for banks whose captures span less than 48 GB: measured (demod kernel, Gsample/s, with / without the
+        // prefetch) 4,096 streams x 6 frames 139 / 114, 8,192 x 6 256 / 214, 4,096 x 28 (40 GB) 131 / 109,
+        // 18,944 x 6 (40 GB) 348 / 348, but 8,192 x 28 (80 GB) 174 / 206 and 18,944 x 14 (93 GB) 320 / 348 — beyond the
+        // reach of the TLBs the hints are dropped and only cost LSU slots and page walks.
+        if (prefetch && k >= 2 && lv && fill + kStageAll <= w0 + kRingRows) {
             const int idx = fill + kStage * (k - 2);
             if (idx + kStage <= stride_i) {
 #pragma unroll
