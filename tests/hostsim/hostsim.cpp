@@ -166,8 +166,9 @@ size_t hostsim_demod_warp(const int16_t* iq, size_t n, int mode, double afc_alph
 
 // whole stream through the BATCHED decomposition (demod_batch_core.cuh): four helper "threads" per
 // symbol (tone x window half) followed by the serial lane.  Same contract as hostsim_demod.
-size_t hostsim_demod_batch(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
-                           double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
+static size_t demod_batch_impl(bool split, const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init,
+                               double init_offset, double* soft_out, size_t cap, double* est_out, double* final_freq,
+                               double* final_tfreq) {
     std::vector<uint32_t> w(n + 64 + 64, 0xDEADBEEFu);
     for (size_t i = 0; i < n; ++i)
         w[64 + i] = (uint32_t)(uint16_t)iq[2 * i] | ((uint32_t)(uint16_t)iq[2 * i + 1] << 16);
@@ -202,7 +203,15 @@ size_t hostsim_demod_batch(const int16_t* iq, size_t n, int mode, double afc_alp
                 double I[31], Q[31];
                 for (int j = 0; j < 31; ++j) unpack_iq(win[30 * half + j], I[j], Q[j]);
                 const ToneLo& t = tone ? r.t2 : r.t1;
-                hg[tone][half] = batch_half_gates(I, Q, t.z, t.q, f, half);
+                if (!split) {
+                    hg[tone][half] = batch_half_gates(I, Q, t.z, t.q, f, half);
+                } else {  // the pipelined kernel's window worker: block sums by two 5-step chains joined by z^5
+                    const cplx A = horner10_split(I, Q, t.z, t.z5), B = horner10_split(I + 10, Q + 10, t.z, t.z5),
+                               Cc = horner10_split(I + 20, Q + 20, t.z, t.z5);
+                    const cplx s0 = {I[0], Q[0]}, s10 = {I[10], Q[10]}, s20 = {I[20], Q[20]}, s30 = {I[30], Q[30]};
+                    hg[tone][half] = half_gates_from_blocks(A, B, Cc, half ? s10 : s0, half ? s20 : s10, half ? s30 : s20,
+                                                            t.z, t.q, f, half);
+                }
             }
         cplx fix1 = {0.0, 0.0}, fix2 = {0.0, 0.0};
         if (first) { fix1 = first_symbol_fix(win, f, r.t1.z); fix2 = first_symbol_fix(win, f, r.t2.z); }
@@ -218,6 +227,19 @@ size_t hostsim_demod_batch(const int16_t* iq, size_t n, int mode, double afc_alp
     if (final_freq) *final_freq = r.freq_offset;
     if (final_tfreq) *final_tfreq = r.timing_freq;
     return ns;
+}
+
+// whole stream through the BATCHED decomposition (kernels_demod_batch.cu)
+size_t hostsim_demod_batch(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
+                           double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
+    return demod_batch_impl(false, iq, n, mode, afc_alpha, have_init, init_offset, soft_out, cap, est_out, final_freq,
+                            final_tfreq);
+}
+// the same with the pipelined kernel's split block sums (kernels_demod_pipe.cu, lanes_per_stream = 128)
+size_t hostsim_demod_pipe_split(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
+                                double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
+    return demod_batch_impl(true, iq, n, mode, afc_alpha, have_init, init_offset, soft_out, cap, est_out, final_freq,
+                            final_tfreq);
 }
 
 // whole stream through the PIPELINED kernel's decomposition (demod_pipe_core.cuh): four quarter "threads" per
