@@ -272,6 +272,33 @@ def test_bank_cli_udp_egress(pkg, cases, tmp_path):
         sk.close()
 
 
+def test_baseline_config0_clean_100_frame_loopback(pkg, ora):
+    """BASELINE.json configs[0]: `opv-mod -S W5NYV -B 100 | opv-demod -r` (clean single-stream loopback).  The capture
+    comes from the TX restatement of opv-mod (pinned to the reference binary in tests/test_oracle.py); the drop-in CLI
+    must write 13,400 bytes, frame n = 000003742697 BBAADD 000000 + (n+i)&0xFF (src/opv-mod.cpp:339-361), identical in
+    batch and streaming mode, every frame "perfect", and equal to the reference process when shipped."""
+    from tools import captures as cap
+
+    iq = cap.clean_bert(100)
+    raw = np.ascontiguousarray(iq).tobytes()
+    want = np.zeros((100, 134), np.uint8)
+    for n in range(100):
+        want[n, :6] = [0x00, 0x00, 0x03, 0x74, 0x26, 0x97]
+        want[n, 6:9] = [0xBB, 0xAA, 0xDD]
+        want[n, 12:] = [(n + i) & 0xFF for i in range(122)]
+    outs = {}
+    for flags in (["-r"], ["-s", "-r"]):
+        p = subprocess.run([pkg.CLI_PATH, *flags], input=raw, capture_output=True)
+        assert p.returncode == 0
+        assert len(p.stdout) == 13400 and p.stdout == want.tobytes(), flags
+        assert b"Summary: 100 frames (100 perfect, 0 errors)" in p.stderr
+        outs[tuple(flags)] = p.stdout
+        if ora.have_ref():
+            ref = subprocess.run([ora.REF_DEMOD, *flags], input=raw, capture_output=True)
+            assert ref.stdout == p.stdout and ref.returncode == p.returncode
+    assert outs[("-r",)] == outs[("-s", "-r")]
+
+
 def test_synth_bank_matches_tx_restatement(pkg, ora):
     """The device generator without impairments reproduces opv-mod's waveform (apart from rare +/-1 LSB
     truncation flips caused by opv-mod's accumulated phase rounding) and decodes to its BERT payloads."""
