@@ -77,6 +77,24 @@ def test_bank_cli_no_cpu_fallback_and_help(built, tmp_path):
     assert not os.path.exists(str(f) + ".frames") or os.path.getsize(str(f) + ".frames") == 0
 
 
+def test_integration_md_stub_compiles_against_header(built, tmp_path):
+    """The binding INTEGRATION.md shows a reference maintainer is real code: it compiles and links against
+    include/opvd.h + libopvd.so as written, and fails loudly (no frames, non-zero exit) without a device."""
+    import torch
+
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = re.search(r"```cpp\n(.*?)```", doc, re.S).group(1)
+    src = tmp_path / "main.cpp"
+    src.write_text(code)
+    exe = tmp_path / "main"
+    libdir = os.path.dirname(built.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", str(src), "-I", os.path.join(ROOT, "include"),
+                    "-L", libdir, "-lopvd", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    if not torch.cuda.is_available():
+        p = subprocess.run([str(exe)], input=b"\0" * 4000, capture_output=True)
+        assert p.returncode != 0 and p.stdout == b"" and b"no CPU fallback" in p.stderr
+
+
 def test_cli_help_contract(built):
     p = subprocess.run([built.CLI_PATH, "-h"], capture_output=True)
     assert p.returncode == 0 and b"-s" in p.stderr and b"-r" in p.stderr and b"-o <hz>" in p.stderr
