@@ -208,6 +208,8 @@ demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         st.n_sym = n_sym0 + (long long)(c.soft_ptr - (soft_row + n_sym0));
         if (!demod_schedule(st, c.pos, mode, avail, final_flag != 0)) break;
         c.origin_rel = (int)(st.origin - row0);
+        asm volatile("" : "+r"(c.origin_rel));  // keep it in a register: ptxas otherwise re-derives it from the constant
+                                                // bank (row_base) in every symbol, an exposed 26-cycle LDC
         const int call_len_i = (int)st.call_len;
         const double call_len_d = (double)st.call_len;
         int b = __double2int_rz(c.pos);  // pos >= 0: truncation == floor (:125)
