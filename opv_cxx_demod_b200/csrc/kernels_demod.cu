@@ -323,6 +323,7 @@ cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodSt
     if (n_streams <= 0) return cudaSuccess;
     int L = lanes_per_stream > 0 ? lanes_per_stream : demod_auto_lanes(n_streams);
     if (L >= 128) return launch_demod_pipe(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    if (L >= 96) return launch_demod_bank(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     if (L >= 64) return launch_demod_batch(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     if (L >= 32) return launch_demod_warp(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     if (L >= 4) return launch_t<1, 2>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);

@@ -1,0 +1,378 @@
+// kernels_demod_bank.cu — A1/A3/A4 for sm_100a, CHANNEL-BANK variant (demod_bank_core.cuh): the kernel for
+// thousands of streams (north-star regime, >= 16,384 streams per GPU = 128 per SM).
+//
+// A CTA of 96 threads owns 32 streams; lane = stream in each of its three warps, so every instruction does 32
+// streams' worth of work and nothing is ever exchanged inside a warp.  The warps are three free-running roles
+// coupled only by named barriers (producer/consumer hand-offs through shared memory), never by a CTA barrier:
+//   warp 0  WINDOW  on-time Horner sums of both tones -> soft symbol + dominant tone -> hands the on-time
+//                   correlations to the AFC warp -> early/late sums of the dominant tone only -> TED, timing
+//                   loop, next position, call schedule (:221-286, :313, :1012-1113)
+//   warp 1  AFC     phase detector, AFC loop, LO steps z (handed back first: the next symbol's Horner needs
+//                   nothing else), then the LO powers z^10, z^20, zeta^40 for the gate combination (:289-310)
+//   warp 2  STAGE   moves the streams' samples from HBM into the transposed shared-memory ring, two batches of
+//                   5 x 32 bytes per lane in flight, 2-4 symbols ahead of the window (flow control through two
+//                   per-stream words in shared memory, no barrier)
+// The AFC chain of symbol n therefore overlaps the early/late + timing half of symbol n on the same SM
+// sub-partition, and the FP64 pipe — the unit that bounds this kernel — sees two independent instruction
+// streams per 32 streams instead of one alternating window/loop phase (round 1: 47 % busy).
+//
+// Sample ring: ring[row][stream], row = sample index mod 256, rows 0..63 mirrored behind row 255 so a 61-row
+// window never wraps; lane s always reads bank s (conflict-free whatever the streams' window positions are).
+// Words are stored with Q's sign bit flipped (offset binary) so Q converts with one integer op + one DADD and I
+// with one I2F.F64.S16 (XU pipe).
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdlib>
+
+#include "demod_bank_core.cuh"
+#include "demod_warp_core.cuh"  // first_symbol_fix_w
+#include "opvd_kernels.cuh"
+
+namespace opvd {
+
+namespace {
+
+constexpr int kSpc = 32;             // streams per CTA
+constexpr int kThreads = 96;         // window, AFC, staging warp
+constexpr int kRingRows = 256;       // samples per stream resident in shared memory (power of two)
+constexpr int kMirrorRows = 64;      // rows 0..63 repeated after row 255
+constexpr int kRows = kRingRows + kMirrorRows;
+constexpr int kChunk = 8;            // samples per 32-byte sector
+constexpr int kBatchChunks = 5;      // chunks per staging batch: 40 samples = one symbol's worth
+constexpr int kBatch = kChunk * kBatchChunks;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kQBias = 0x80000000u;
+
+enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3 };  // named barriers (0 is __syncthreads)
+enum : int { kFlagTone1 = 1, kFlagFirst = 2, kFlagLive = 4, kFlagExit = 8 };
+
+struct __align__(16) BankSmem {
+    uint32_t ring[kRows][kSpc];   // 40 KB
+    double o[4][kSpc];            // WINDOW -> AFC: O1.r, O1.i, O2.r, O2.i
+    double z[4][kSpc];            // AFC -> WINDOW: z1.r, z1.i, z2.r, z2.i
+    double pw[10][kSpc];          // AFC -> WINDOW: q1, q2, qq1, qq2, zeta40
+    int flags[kSpc];              // WINDOW -> AFC: kFlag*
+    int w0[kSpc];                 // WINDOW -> STAGE: row-relative sample index of window slot 0 of the current symbol
+    int fill[kSpc];               // STAGE -> WINDOW: samples [.., fill) of the stream's row are in the ring
+    int live[kSpc];               // WINDOW -> STAGE: stream still has symbols to demodulate in this launch
+    int exit_flag;                // WINDOW -> STAGE
+};
+
+template <int ID>
+__device__ __forceinline__ void bar_sync() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
+template <int ID>
+__device__ __forceinline__ void bar_arrive() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
+__device__ __forceinline__ int ld_vol(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void st_vol(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
+
+// ring word (I raw, Q offset-binary) -> doubles.  I always converts with one I2F.F64.S16 (XU pipe, 8 cycles per warp
+// instruction, one issue slot); Q either the same way (after undoing the offset) or with the 2^52 bias trick (two
+// integer-pipe instructions + one DADD on the FP64 pipe).  QX picks the split by window slot: the kernel is bound by
+// issue slots, the FP64 pipe and the XU pipe at nearly the same level, so the split balances the three.
+//   QX = 0  every Q through the bias trick      QX = 1  odd slots through XU      QX = 2  every Q through XU
+template <int QX>
+__device__ __forceinline__ void unpack_ring(uint32_t w, int k, double& I, double& Q) {
+    I = (double)(int16_t)(w & 0xFFFFu);
+    if (QX == 2 || (QX == 1 && (k & 1)))
+        Q = (double)(int16_t)((w >> 16) ^ 0x8000u);
+    else
+        Q = __hiloint2double(0x43300000, (int)(w >> 16)) - 4503599627403264.0;  // 2^52 + 2^15
+}
+
+__device__ __forceinline__ void ldg256(const uint32_t* p, uint4& a, uint4& b) {  // read-once, 32-byte aligned
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ uint4 ldg128(const uint32_t* p) {
+    uint4 a;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+                 : "l"(p));
+    return a;
+}
+
+// 8 consecutive samples starting at row index idx (multiple of 8); rows are 16-byte aligned and a multiple of
+// 4 samples long, so only the last chunk of a row can be partial
+__device__ __forceinline__ void chunk_load(const uint32_t* row, int idx, int stride, bool wide, uint4& a, uint4& b) {
+    if (idx + kChunk <= stride) {
+        if (wide) {
+            ldg256(row + idx, a, b);
+        } else {
+            a = ldg128(row + idx);
+            b = ldg128(row + idx + 4);
+        }
+    } else {
+        a = (idx + 4 <= stride) ? ldg128(row + idx) : make_uint4(0u, 0u, 0u, 0u);
+        b = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+__device__ __forceinline__ void chunk_store(BankSmem& sm, int s, int idx, uint4 a, uint4 b) {
+    const int r = idx & (kRingRows - 1);
+    const uint32_t w[8] = {a.x ^ kQBias, a.y ^ kQBias, a.z ^ kQBias, a.w ^ kQBias,
+                           b.x ^ kQBias, b.y ^ kQBias, b.z ^ kQBias, b.w ^ kQBias};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm.ring[r + j][s] = w[j];
+    if (r < kMirrorRows) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm.ring[kRingRows + r + j][s] = w[j];
+    }
+}
+
+// early-gate correction for the first symbol of a call (rare: kept out of line)
+__device__ __noinline__ cplx first_fix_cold(const uint32_t* win, double f, cplx z) {
+    return first_symbol_fix_w([&](int kk) { return win[kk * kSpc] ^ kQBias; }, f, z);
+}
+// call scheduling out of line; everything it touches by reference lives in local memory
+__device__ __noinline__ bool schedule_cold(DemodState& st, int mode, long long avail, bool final_flag) {
+    double pos = st.pos;
+    const bool live = demod_schedule(st, pos, mode, avail, final_flag);
+    st.pos = pos;
+    return live;
+}
+
+}  // namespace
+
+template <int QX>
+__global__ void __launch_bounds__(kThreads, 4)
+demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
+                  int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BankSmem& sm = *reinterpret_cast<BankSmem*>(smem_raw);
+    const int s = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const int stream_raw = blockIdx.x * kSpc + s;
+    const bool valid = stream_raw < n_streams;
+    const int stream = valid ? stream_raw : n_streams - 1;
+    const long long row0 = sb.row_base;
+
+    if (role == 0) {
+        // ================================================================= WINDOW
+        DemodState st = dstate[stream];  // local memory: only the scheduler touches it
+        const long long avail = sb.avail[stream];
+        double* const soft_row = so.soft + (long long)stream * so.stride - so.base;
+        double* soft_ptr = soft_row + st.n_sym;
+        const long long n_sym0 = st.n_sym, origin0 = st.origin;
+        double timing_freq = st.timing_freq;
+        bool live = valid && schedule_cold(st, mode, avail, final_flag != 0);
+        double pos = st.pos;
+        int sym_in_call = st.sym_in_call;
+        double call_len_d = (double)st.call_len;
+        int origin_rel = (int)(st.origin - row0);
+        int w0 = 0;
+        double f = 0.0;
+        if (live) {
+            const int b = __double2int_rz(pos);  // pos >= 0: truncation == floor (:125)
+            f = pos - (double)b;
+            w0 = origin_rel + b - kWinLead;
+        }
+        sm.w0[s] = w0;
+        sm.live[s] = live ? 1 : 0;
+        if (s == 0) sm.exit_flag = 0;
+        __syncthreads();  // (1) symbol 0 published
+        bool any_live = __any_sync(kFull, live);
+        while (any_live) {
+            const bool first = sym_in_call == 0;
+            // ---- LO steps of this symbol
+            bar_sync<kBarZ>();
+            BankLo lo;
+            lo.z1 = {sm.z[0][s], sm.z[1][s]};
+            lo.z2 = {sm.z[2][s], sm.z[3][s]};
+            lo.inc1 = 0.0; lo.inc2 = 0.0;
+            // ---- the window must be in the ring (normally true: the staging warp runs 2-4 symbols ahead)
+            while (!__all_sync(kFull, !live || ld_vol(&sm.fill[s]) >= w0 + kWin)) {}
+            __threadfence_block();
+            const uint32_t* const win = &sm.ring[w0 & (kRingRows - 1)][s];
+            auto slot = [&](int k, double& I, double& Q) { unpack_ring<QX>(win[k * kSpc], k, I, Q); };
+            // ---- on-time block sums, both tones
+            cplx A[4], B[4], s10, s20, s40;
+            bank_on_blocks(slot, lo.z1, lo.z2, A, B, s10, s20, s40);
+            // ---- LO powers, gate combination, soft decision
+            bar_sync<kBarPow>();
+            BankPow pw;
+            pw.q1 = {sm.pw[0][s], sm.pw[1][s]};
+            pw.q2 = {sm.pw[2][s], sm.pw[3][s]};
+            pw.qq1 = {sm.pw[4][s], sm.pw[5][s]};
+            pw.qq2 = {sm.pw[6][s], sm.pw[7][s]};
+            pw.zeta40 = {sm.pw[8][s], sm.pw[9][s]};
+            BankOnTime on;
+            bank_on_time(slot, f, lo, pw, A, B, s10, s20, s40, on);
+            const bool tone1 = on.eO1 > on.eO2;  // :272, :291
+            sm.o[0][s] = on.O1.r; sm.o[1][s] = on.O1.i; sm.o[2][s] = on.O2.r; sm.o[3][s] = on.O2.i;
+            sm.flags[s] = (tone1 ? kFlagTone1 : 0) | (first ? kFlagFirst : 0) | (live ? kFlagLive : 0);
+            bar_arrive<kBarO>();  // the AFC warp takes it from here
+            if (live) *soft_ptr++ = on.eO2 - on.eO1;  // :268
+            // ---- early / late gates of the dominant tone, timing loop
+            cplx fixE = {0.0, 0.0};
+            if (first && live) fixE = first_fix_cold(win, f, tone1 ? lo.z1 : lo.z2);  // :237, once per call
+            double eE, eL;
+            bank_early_late(slot, f, tone1, lo, pw, on, fixE, eE, eL);
+            if (live) {
+                bank_timing(eE, eL, timing_freq, pos, g_fm);
+                sym_in_call = 1;  // any non-zero value: the open call has produced symbols
+                // ---- next symbol of this stream
+                if (!((pos + 40.0) + 10.0 < call_len_d)) {  // :221 fails: close the call, maybe open the next
+                    st.n_sym = (long long)(soft_ptr - soft_row);
+                    st.sym_in_call = sym_in_call;
+                    st.pos = pos;
+                    live = schedule_cold(st, mode, avail, final_flag != 0);
+                    pos = st.pos;
+                    sym_in_call = st.sym_in_call;
+                    call_len_d = (double)st.call_len;
+                    origin_rel = (int)(st.origin - row0);
+                }
+                if (live) {
+                    const int b2 = __double2int_rz(pos);
+                    w0 = origin_rel + b2 - kWinLead;
+                    f = pos - (double)b2;
+                    st_vol(&sm.w0[s], w0);
+                } else {
+                    st_vol(&sm.live[s], 0);
+                }
+            }
+            any_live = __any_sync(kFull, live);
+        }
+        // ---- tell the other roles to stop
+        sm.flags[s] = kFlagExit;
+        st_vol(&sm.exit_flag, 1);
+        bar_arrive<kBarO>();
+        // ---- persist the streams' state: this warp writes the record, the AFC warp then patches its fields
+        if (valid) {
+            st.n_sym = (long long)(soft_ptr - soft_row);
+            st.sym_in_call = sym_in_call;
+            st.pos = pos; st.timing_freq = timing_freq;
+            DemodState* d = dstate + stream;
+            d->pos = st.pos; d->timing_freq = st.timing_freq; d->origin = st.origin; d->call_len = st.call_len;
+            d->n_sym = st.n_sym; d->sym_in_call = st.sym_in_call; d->flags = st.flags;
+            unsigned long long dsym = (unsigned long long)(st.n_sym - n_sym0);
+            unsigned long long dsmp = (unsigned long long)(st.origin - origin0);
+            if (st.flags & kFlagDone) dsmp = (unsigned long long)(avail - origin0);
+            if (dsym) atomicAdd(&counters[kCtrSymbols], dsym);
+            if (dsmp) atomicAdd(&counters[kCtrSamples], dsmp);
+        }
+    } else if (role == 1) {
+        // ================================================================= AFC
+        const DemodState* d0 = dstate + stream;
+        BankAfc afc = {d0->freq_offset, d0->ph1, d0->ph2, d0->p1, d0->p2};
+        BankLo lo;
+        BankPow pw;
+        {
+            double d;
+            const cplx zeta = bank_zeta_general(afc.freq_offset, d);  // a -o offset may exceed the fast range
+            bank_lo_from_zeta(zeta, d, lo, g_fm);
+            bank_pow_from_zeta(zeta, pw, g_bk);
+        }
+        __syncthreads();  // (1)
+        auto publish_z = [&]() {
+            sm.z[0][s] = lo.z1.r; sm.z[1][s] = lo.z1.i; sm.z[2][s] = lo.z2.r; sm.z[3][s] = lo.z2.i;
+            bar_arrive<kBarZ>();
+        };
+        auto publish_pow = [&]() {
+            sm.pw[0][s] = pw.q1.r; sm.pw[1][s] = pw.q1.i; sm.pw[2][s] = pw.q2.r; sm.pw[3][s] = pw.q2.i;
+            sm.pw[4][s] = pw.qq1.r; sm.pw[5][s] = pw.qq1.i; sm.pw[6][s] = pw.qq2.r; sm.pw[7][s] = pw.qq2.i;
+            sm.pw[8][s] = pw.zeta40.r; sm.pw[9][s] = pw.zeta40.i;
+            bar_arrive<kBarPow>();
+        };
+        publish_z();
+        publish_pow();
+        for (;;) {
+            bar_sync<kBarO>();
+            const int fl = sm.flags[s];
+            if (fl & kFlagExit) break;  // warp-uniform: the window warp sets it on every lane
+            const cplx O1 = {sm.o[0][s], sm.o[1][s]}, O2 = {sm.o[2][s], sm.o[3][s]};
+            // no AFC update on the first symbol of a call (:289): same LO steps next symbol
+            const bool update = (fl & kFlagLive) && !(fl & kFlagFirst);
+            cplx zeta = {1.0, 0.0};
+            if (fl & kFlagLive) {
+                bank_afc(afc, O1, O2, (fl & kFlagTone1) != 0, pw.zeta40, lo.inc1, lo.inc2, (fl & kFlagFirst) != 0,
+                         afc_alpha, g_fm);
+                if (update) {
+                    double d;
+                    zeta = bank_zeta_fast(afc.freq_offset, d, g_fm);  // |offset| <= 2 kHz after the clamp (:303)
+                    bank_lo_from_zeta(zeta, d, lo, g_fm);
+                }
+            }
+            publish_z();  // z goes out first: the next symbol's Horner needs nothing else
+            if (update) bank_pow_from_zeta(zeta, pw, g_bk);
+            publish_pow();
+        }
+        __syncthreads();  // (2) the window warp has written the records
+        if (valid) {
+            DemodState* d = dstate + stream;
+            d->freq_offset = afc.freq_offset; d->ph1 = afc.ph1; d->ph2 = afc.ph2; d->p1 = afc.p1; d->p2 = afc.p2;
+        }
+        return;
+    } else {
+        // ================================================================= STAGE
+        const uint32_t* __restrict__ row = sb.iq + (long long)stream * sb.stride;  // row[r] = absolute sample row0 + r
+        const int stride_i = (int)sb.stride;
+        const bool wide = ((reinterpret_cast<uintptr_t>(sb.iq) | (uintptr_t)(sb.stride * 4)) & 31u) == 0;
+        sm.fill[s] = -(1 << 30);
+        __syncthreads();  // (1)
+        int req;  // samples [.., req) of this lane's row have been requested (multiple of 8)
+        {
+            const int w0 = sm.w0[s];
+            req = (w0 < 0 ? 0 : w0) & ~(kChunk - 1);
+        }
+        uint4 bufA[2 * kBatchChunks], bufB[2 * kBatchChunks];
+        int idxA = -1, idxB = -1;  // row index of the batch held in the buffer (-1: empty)
+        auto request = [&](uint4 (&buf)[2 * kBatchChunks], int& idx) {
+            const int w0 = ld_vol(&sm.w0[s]);
+            const bool can = ld_vol(&sm.live[s]) != 0 && req + kBatch <= w0 + kRingRows - kChunk && req < stride_i;
+            idx = -1;
+            if (can) {
+#pragma unroll
+                for (int c = 0; c < kBatchChunks; ++c) chunk_load(row, req + kChunk * c, stride_i, wide, buf[2 * c], buf[2 * c + 1]);
+                idx = req;
+                req += kBatch;
+            }
+            return can;
+        };
+        auto retire = [&](uint4 (&buf)[2 * kBatchChunks], int& idx) {
+            const bool had = idx >= 0;
+            if (had) {
+#pragma unroll
+                for (int c = 0; c < kBatchChunks; ++c) chunk_store(sm, s, idx + kChunk * c, buf[2 * c], buf[2 * c + 1]);
+                __threadfence_block();
+                st_vol(&sm.fill[s], idx + kBatch);
+                idx = -1;
+            }
+            return had;
+        };
+        for (;;) {
+            bool work = request(bufA, idxA);
+            work |= retire(bufB, idxB);
+            work |= request(bufB, idxB);
+            work |= retire(bufA, idxA);
+            if (!__any_sync(kFull, work)) {
+                if (ld_vol(&sm.exit_flag)) break;
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();  // (2)
+        return;
+    }
+    __syncthreads();  // (2) window warp
+}
+
+template <int QX>
+static cudaError_t launch_bank_t(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams, int mode,
+                                 int final_flag, double afc_alpha, unsigned long long* counters, cudaStream_t st) {
+    const size_t smem = sizeof(BankSmem);
+    cudaError_t e = cudaFuncSetAttribute(demod_bank_kernel<QX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (n_streams + kSpc - 1) / kSpc;
+    demod_bank_kernel<QX><<<grid, kThreads, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
+                              int mode, int final_flag, double afc_alpha, unsigned long long* counters,
+                              cudaStream_t st) {
+    // OPVD_BANK_QX: development switch for the conversion split (see unpack_ring); every value gives identical results
+    static const int qx = [] { const char* e = getenv("OPVD_BANK_QX"); return e ? atoi(e) : 1; }();
+    if (qx == 0) return launch_bank_t<0>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    if (qx == 2) return launch_bank_t<2>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    return launch_bank_t<1>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+}
+
+}  // namespace opvd

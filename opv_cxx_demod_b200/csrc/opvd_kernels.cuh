@@ -71,6 +71,12 @@ cudaError_t launch_demod_batch(const StreamBuffers& sb, const SoftBuffers& so, D
                                int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                                cudaStream_t st);
 
+// channel-bank variant (kernels_demod_bank.cu): 32 streams per 96-thread CTA, three free-running role warps;
+// selected by launch_demod for lanes_per_stream == 96
+cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
+                              int mode, int final_flag, double afc_alpha, unsigned long long* counters,
+                              cudaStream_t st);
+
 // pipelined batched variant (kernels_demod_pipe.cu); selected by launch_demod for lanes_per_stream == 128
 cudaError_t launch_demod_pipe(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,

@@ -11,6 +11,7 @@
 #include "../../opv_cxx_demod_b200/csrc/demod_warp_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/demod_batch_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/demod_pipe_core.cuh"
+#include "../../opv_cxx_demod_b200/csrc/demod_bank_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/demod_coherent_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/est_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/track_core.cuh"
@@ -297,6 +298,75 @@ size_t hostsim_demod_pipe(const int16_t* iq, size_t n, int mode, double afc_alph
     if (est_out) *est_out = est;
     if (final_freq) *final_freq = r.freq_offset;
     if (final_tfreq) *final_tfreq = r.timing_freq;
+    return ns;
+}
+
+// whole stream through the CHANNEL-BANK decomposition (demod_bank_core.cuh, kernels_demod_bank.cu): on-time sums of
+// both tones, early/late sums of the dominant tone only, LO powers from one zeta chain.  Same contract as hostsim_demod.
+size_t hostsim_demod_bank(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
+                          double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
+    std::vector<uint32_t> w(n + 64 + 64, 0xDEADBEEFu);
+    for (size_t i = 0; i < n; ++i)
+        w[64 + i] = (uint32_t)(uint16_t)iq[2 * i] | ((uint32_t)(uint16_t)iq[2 * i + 1] << 16);
+    const uint32_t* base = w.data() + 64;
+
+    DemodState st;
+    demod_state_init(st);
+    double est = 0.0;
+    if (mode == kModeBatch) {
+        est = hostsim_estimate(iq, n);
+        st.freq_offset = est;
+    } else if (have_init) {
+        st.freq_offset = init_offset;
+    } else if (n >= (size_t)kChunkSamples) {
+        est = hostsim_estimate(iq, kChunkSamples);
+        st.freq_offset = est;
+    }
+    st.flags |= kFlagEstDone;
+    BankAfc afc = {st.freq_offset, st.ph1, st.ph2, st.p1, st.p2};
+    BankLo lo;
+    BankPow pw;
+    {
+        double d;
+        const cplx zeta = bank_zeta_general(afc.freq_offset, d);
+        bank_lo_from_zeta(zeta, d, lo, g_fm);
+        bank_pow_from_zeta(zeta, pw, g_bk);
+    }
+    double pos = st.pos, timing_freq = st.timing_freq;
+    size_t ns = 0;
+    while (demod_schedule(st, pos, mode, (int64_t)n, true)) {
+        const int64_t b = (int64_t)pos;
+        const double f = pos - (double)b;
+        const uint32_t* win = base + st.origin + b - kWinLead;
+        const bool first = st.sym_in_call == 0;
+        auto slot = [&](int k, double& I, double& Q) { unpack_iq(win[k], I, Q); };
+        cplx A[4], B[4], s10, s20, s40;
+        bank_on_blocks(slot, lo.z1, lo.z2, A, B, s10, s20, s40);
+        BankOnTime on;
+        bank_on_time(slot, f, lo, pw, A, B, s10, s20, s40, on);
+        const bool tone1 = on.eO1 > on.eO2;
+        const double soft = on.eO2 - on.eO1;
+        cplx fixE = {0.0, 0.0};
+        if (first) fixE = first_symbol_fix(win, f, tone1 ? lo.z1 : lo.z2);
+        double eE, eL;
+        bank_early_late(slot, f, tone1, lo, pw, on, fixE, eE, eL);
+        bank_timing(eE, eL, timing_freq, pos, g_fm);
+        // AFC role
+        bank_afc(afc, on.O1, on.O2, tone1, pw.zeta40, lo.inc1, lo.inc2, first, afc_alpha, g_fm);
+        if (!first) {
+            double d;
+            const cplx zeta = bank_zeta_fast(afc.freq_offset, d, g_fm);
+            bank_lo_from_zeta(zeta, d, lo, g_fm);
+            bank_pow_from_zeta(zeta, pw, g_bk);
+        }
+        st.sym_in_call++;
+        if (ns < cap) soft_out[ns] = soft;
+        ++ns;
+        st.n_sym++;
+    }
+    if (est_out) *est_out = est;
+    if (final_freq) *final_freq = afc.freq_offset;
+    if (final_tfreq) *final_tfreq = timing_freq;
     return ns;
 }
 

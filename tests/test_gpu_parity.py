@@ -55,7 +55,7 @@ def _run_bank(pkg, caps, streaming, **kw):
     return bank
 
 
-@pytest.mark.parametrize("lanes", [1, 2, 4, 32, 64, 128])
+@pytest.mark.parametrize("lanes", [1, 2, 4, 32, 64, 96, 128])
 @pytest.mark.parametrize("streaming", [False, True])
 def test_all_cases_one_bank_vs_oracle_and_golden(streaming, lanes, pkg, cases, ora):
     """All standard captures as ONE ragged multi-stream bank: frames / events / soft / offsets per stream,
@@ -486,7 +486,7 @@ def test_abi_error_behaviour(pkg):
     assert L.opvd_strerror(-3).decode() and L.opvd_strerror(-5).decode()
 
 
-@pytest.mark.parametrize("lanes", [32, 64, 128])
+@pytest.mark.parametrize("lanes", [32, 64, 96, 128])
 def test_attached_rows_16_byte_aligned_only(lanes, pkg, ora):
     """opvd_attach_device_iq promises 16-byte row alignment only (stride % 4 == 0): rows whose stride is 4 (mod 8)
     samples are not 32-byte aligned, so the 256-bit staging loads must fall back to 128-bit ones."""

@@ -31,6 +31,8 @@ def sim():
     H.hostsim_demod_warp.argtypes = H.hostsim_demod.argtypes
     H.hostsim_demod_batch.restype = C.c_size_t
     H.hostsim_demod_batch.argtypes = H.hostsim_demod.argtypes
+    H.hostsim_demod_bank.restype = C.c_size_t
+    H.hostsim_demod_bank.argtypes = H.hostsim_demod.argtypes
     H.hostsim_demod_pipe_split.restype = C.c_size_t
     H.hostsim_demod_pipe_split.argtypes = H.hostsim_demod.argtypes
     H.hostsim_demod_pipe.restype = C.c_size_t
@@ -50,7 +52,7 @@ NAMES = ["clean5", "clean12_call", "awgn14", "awgn8", "awgn4", "cfo_p1200_delay"
 
 @pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("variant", ["lane", "warp", "batch", "pipe_split", "pipe"])
+@pytest.mark.parametrize("variant", ["lane", "warp", "batch", "bank", "pipe_split", "pipe"])
 def test_device_arithmetic_vs_oracle(name, mode, variant, cases, ora, sim):
     iq = cases[name]
     a = np.ascontiguousarray(iq, np.int16).reshape(-1)
@@ -58,7 +60,7 @@ def test_device_arithmetic_vs_oracle(name, mode, variant, cases, ora, sim):
     ref = ora.run(iq, bool(mode))
     soft = np.zeros(n // 40 + 16)
     est, ff, tf = C.c_double(), C.c_double(), C.c_double()
-    fn = {"lane": sim.hostsim_demod, "warp": sim.hostsim_demod_warp, "batch": sim.hostsim_demod_batch,
+    fn = {"lane": sim.hostsim_demod, "warp": sim.hostsim_demod_warp, "batch": sim.hostsim_demod_batch, "bank": sim.hostsim_demod_bank,
           "pipe_split": sim.hostsim_demod_pipe_split, "pipe": sim.hostsim_demod_pipe}[variant]
     ns = fn(a.ctypes.data, n, mode, 0.001, 0, 0.0, soft.ctypes.data, soft.size, C.byref(est),
                            C.byref(ff), C.byref(tf))
