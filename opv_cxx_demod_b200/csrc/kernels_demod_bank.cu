@@ -92,18 +92,20 @@ __device__ __forceinline__ uint4 ldg128(const uint32_t* p) {
     return a;
 }
 
-// 8 consecutive samples starting at row index idx (multiple of 8); rows are 16-byte aligned and a multiple of
-// 4 samples long, so only the last chunk of a row can be partial
-__device__ __forceinline__ void chunk_load(const uint32_t* row, int idx, int stride, bool wide, uint4& a, uint4& b) {
-    if (idx + kChunk <= stride) {
+// 8 consecutive samples starting at rel (multiple of 8).  A ring is a multiple of 64 samples long, so a chunk never
+// straddles its end; linear rows are 16-byte aligned and a multiple of 4 samples long, so only their last chunk can
+// be partial.
+__device__ __forceinline__ void chunk_load(const RowView& v, int rel, bool wide, uint4& a, uint4& b) {
+    const uint32_t* p = v.row + v.phys(rel);
+    if (rel + kChunk <= v.rel_end) {
         if (wide) {
-            ldg256(row + idx, a, b);
+            ldg256(p, a, b);
         } else {
-            a = ldg128(row + idx);
-            b = ldg128(row + idx + 4);
+            a = ldg128(p);
+            b = ldg128(p + 4);
         }
     } else {
-        a = (idx + 4 <= stride) ? ldg128(row + idx) : make_uint4(0u, 0u, 0u, 0u);
+        a = (rel + 4 <= v.rel_end) ? ldg128(p) : make_uint4(0u, 0u, 0u, 0u);
         b = make_uint4(0u, 0u, 0u, 0u);
     }
 }
@@ -143,21 +145,23 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     const int stream_raw = blockIdx.x * kSpc + s;
     const bool valid = stream_raw < n_streams;
     const int stream = valid ? stream_raw : n_streams - 1;
-    const long long row0 = sb.row_base;
 
     if (role == 0) {
         // ================================================================= WINDOW
         DemodState st = dstate[stream];  // local memory: only the scheduler touches it
         const long long avail = sb.avail[stream];
-        double* const soft_row = so.soft + (long long)stream * so.stride - so.base;
-        double* soft_ptr = soft_row + st.n_sym;
+        double* const soft_row = so.soft + (long long)stream * so.stride;
+        const int soft_wrap = so.ring ? (int)so.stride : 0x7fffffff;
+        int soft_idx = (int)soft_pos(so, st.n_sym);  // row position of the next soft symbol
+        int n_new = 0;                               // symbols produced by this launch
         const long long n_sym0 = st.n_sym, origin0 = st.origin;
+        const long long base_abs = make_row_view(sb, stream, st.origin).base_abs;
         double timing_freq = st.timing_freq;
         bool live = valid && schedule_cold(st, mode, avail, final_flag != 0);
         double pos = st.pos;
         int sym_in_call = st.sym_in_call;
         double call_len_d = (double)st.call_len;
-        int origin_rel = (int)(st.origin - row0);
+        int origin_rel = (int)(st.origin - base_abs);
         int w0 = 0;
         double f = 0.0;
         if (live) {
@@ -200,7 +204,11 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
             sm.o[0][s] = on.O1.r; sm.o[1][s] = on.O1.i; sm.o[2][s] = on.O2.r; sm.o[3][s] = on.O2.i;
             sm.flags[s] = (tone1 ? kFlagTone1 : 0) | (first ? kFlagFirst : 0) | (live ? kFlagLive : 0);
             bar_arrive<kBarO>();  // the AFC warp takes it from here
-            if (live) *soft_ptr++ = on.eO2 - on.eO1;  // :268
+            if (live) {
+                soft_row[soft_idx] = on.eO2 - on.eO1;  // :268
+                if (++soft_idx == soft_wrap) soft_idx = 0;
+                ++n_new;
+            }
             // ---- early / late gates of the dominant tone, timing loop
             cplx fixE = {0.0, 0.0};
             if (first && live) fixE = first_fix_cold(win, f, tone1 ? lo.z1 : lo.z2);  // :237, once per call
@@ -211,14 +219,14 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
                 sym_in_call = 1;  // any non-zero value: the open call has produced symbols
                 // ---- next symbol of this stream
                 if (!((pos + 40.0) + 10.0 < call_len_d)) {  // :221 fails: close the call, maybe open the next
-                    st.n_sym = (long long)(soft_ptr - soft_row);
+                    st.n_sym = n_sym0 + n_new;
                     st.sym_in_call = sym_in_call;
                     st.pos = pos;
                     live = schedule_cold(st, mode, avail, final_flag != 0);
                     pos = st.pos;
                     sym_in_call = st.sym_in_call;
                     call_len_d = (double)st.call_len;
-                    origin_rel = (int)(st.origin - row0);
+                    origin_rel = (int)(st.origin - base_abs);
                 }
                 if (live) {
                     const int b2 = __double2int_rz(pos);
@@ -237,9 +245,10 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         bar_arrive<kBarO>();
         // ---- persist the streams' state: this warp writes the record, the AFC warp then patches its fields
         if (valid) {
-            st.n_sym = (long long)(soft_ptr - soft_row);
+            st.n_sym = n_sym0 + n_new;
             st.sym_in_call = sym_in_call;
             st.pos = pos; st.timing_freq = timing_freq;
+            so.n_sym[stream] = st.n_sym;
             DemodState* d = dstate + stream;
             d->pos = st.pos; d->timing_freq = st.timing_freq; d->origin = st.origin; d->call_len = st.call_len;
             d->n_sym = st.n_sym; d->sym_in_call = st.sym_in_call; d->flags = st.flags;
@@ -303,8 +312,7 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         return;
     } else {
         // ================================================================= STAGE
-        const uint32_t* __restrict__ row = sb.iq + (long long)stream * sb.stride;  // row[r] = absolute sample row0 + r
-        const int stride_i = (int)sb.stride;
+        const RowView view = make_row_view(sb, stream, dstate[stream].origin);  // same base as the window warp
         const bool wide = ((reinterpret_cast<uintptr_t>(sb.iq) | (uintptr_t)(sb.stride * 4)) & 31u) == 0;
         sm.fill[s] = -(1 << 30);
         __syncthreads();  // (1)
@@ -317,11 +325,11 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         int idxA = -1, idxB = -1;  // row index of the batch held in the buffer (-1: empty)
         auto request = [&](uint4 (&buf)[2 * kBatchChunks], int& idx) {
             const int w0 = ld_vol(&sm.w0[s]);
-            const bool can = ld_vol(&sm.live[s]) != 0 && req + kBatch <= w0 + kRingRows - kChunk && req < stride_i;
+            const bool can = ld_vol(&sm.live[s]) != 0 && req + kBatch <= w0 + kRingRows - kChunk && req < view.rel_end;
             idx = -1;
             if (can) {
 #pragma unroll
-                for (int c = 0; c < kBatchChunks; ++c) chunk_load(row, req + kChunk * c, stride_i, wide, buf[2 * c], buf[2 * c + 1]);
+                for (int c = 0; c < kBatchChunks; ++c) chunk_load(view, req + kChunk * c, wide, buf[2 * c], buf[2 * c + 1]);
                 idx = req;
                 req += kBatch;
             }

@@ -22,8 +22,8 @@ demod_coherent_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__
     DemodState st = dstate[stream];
     if (st.flags & kFlagDone) return;
     const long long avail = sb.avail[stream];
-    const uint4* row = reinterpret_cast<const uint4*>(sb.iq + (long long)stream * sb.stride - sb.row_base);
-    double* soft_row = so.soft + (long long)stream * so.stride - so.base;
+    const uint4* row = reinterpret_cast<const uint4*>(sb.iq + (long long)stream * sb.stride);  // batch mode: always a linear row
+    double* soft_row = so.soft + (long long)stream * so.stride;
     CoherentState cs;
     coherent_init(cs, st.freq_offset, afc_alpha, pll_bw_hz);  // freq_offset = estimate (:1148-1149)
     const long long n_sym = avail / kSps;
@@ -44,6 +44,7 @@ demod_coherent_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__
     st.origin = avail;
     st.flags |= kFlagDone;
     dstate[stream] = st;
+    so.n_sym[stream] = n_sym;
     if (n_sym) atomicAdd(&counters[kCtrSymbols], (unsigned long long)n_sym);
     if (avail) atomicAdd(&counters[kCtrSamples], (unsigned long long)avail);
 }

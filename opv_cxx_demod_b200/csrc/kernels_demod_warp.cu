@@ -57,20 +57,22 @@ struct WarpCtx {
     double freq_offset, pos, timing_freq, ph_own, afc_alpha;
     const uint32_t* ring;
     uint32_t ring_s;
-    const uint32_t* row;
-    int stride_i, avail_rel, origin_rel;
+    RowView view;        // this stream's sample row (linear or ring) for this launch
+    int avail_rel, origin_rel;
     int issued_s;        // samples [.., issued_s) of the row have been requested (multiple of 64); < 0: ring not primed
     int lane, lane_slot, tone_base;
-    double* soft_ptr;    // where the next soft symbol goes (lane 0 stores)
+    double* soft_row;    // soft-symbol row of this stream (linear or ring)
+    int soft_idx, soft_wrap, n_new;  // row position of the next soft symbol (lane 0 stores), ring length, symbols produced
 
     // request the next 64-sample slot: lanes 0-15 copy 16 bytes each (slot 0 of the ring also feeds the mirror
     // behind the ring's end, so a window never wraps)
     __device__ __forceinline__ void issue_slot() {
         const int p = (issued_s >> kSlotShift) & (kNumSlots - 1);
         const int off = issued_s + 4 * lane;
-        if (lane < 16 && off + 4 <= stride_i) {  // rows are a multiple of 4 samples long
-            cp_async16(ring_s + p * kSlotBytes + 16 * lane, row + off);
-            if (p == 0) cp_async16(ring_s + kNumSlots * kSlotBytes + 16 * lane, row + off);
+        if (lane < 16 && off + 4 <= view.rel_end) {  // linear rows are a multiple of 4 samples long; a ring (a multiple
+            const uint32_t* src = view.row + view.phys(off);  // of 64) never splits a 64-sample slot
+            cp_async16(ring_s + p * kSlotBytes + 16 * lane, src);
+            if (p == 0) cp_async16(ring_s + kNumSlots * kSlotBytes + 16 * lane, src);
         }
         issued_s += kSlotSamples;
     }
@@ -139,8 +141,9 @@ struct WarpCtx {
         const double eE2 = __shfl_sync(kFull, nrm, 16 + kWarpGateLaneE), eL2 = __shfl_sync(kFull, nrm, 16 + kWarpGateLaneL);
         bool tone1;
         const double soft = warp_uniform_timing(e1, e2, eE1, eL1, eE2, eL2, timing_freq, pos, tone1, K);
-        if (lane == 0) *soft_ptr = soft;
-        ++soft_ptr;
+        if (lane == 0) soft_row[soft_idx] = soft;
+        if (++soft_idx == soft_wrap) soft_idx = 0;
+        ++n_new;
 
         // ---- next symbol's samples (its window is already in the ring, see ring_maintain)
         const int b_next = __double2int_rz(pos);  // pos >= 0: truncation == floor (:125)
@@ -181,12 +184,13 @@ demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
 
     DemodState st = dstate[stream];
     const long long avail = sb.avail[stream];
-    const long long row0 = sb.row_base;
-    c.row = sb.iq + (long long)stream * sb.stride;  // row[r] holds absolute sample row0 + r
-    c.stride_i = (int)sb.stride;
+    c.view = make_row_view(sb, stream, st.origin);
+    const long long row0 = c.view.base_abs;  // rel = absolute sample index - row0
     c.avail_rel = (int)(avail - row0);
-    double* const soft_row = so.soft + (long long)stream * so.stride - so.base;
-    c.soft_ptr = soft_row + st.n_sym;
+    c.soft_row = so.soft + (long long)stream * so.stride;
+    c.soft_wrap = so.ring ? (int)so.stride : 0x7fffffff;
+    c.soft_idx = (int)soft_pos(so, st.n_sym);
+    c.n_new = 0;
     c.afc_alpha = afc_alpha;
 
     warp_lane_init(c.wl, lane, c.K);
@@ -205,7 +209,7 @@ demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     const long long n_sym0 = st.n_sym, origin0 = st.origin;
     for (;;) {
         // ---- call boundary (warp-uniform slow path): close / open demodulate() calls (:1012-1113)
-        st.n_sym = n_sym0 + (long long)(c.soft_ptr - (soft_row + n_sym0));
+        st.n_sym = n_sym0 + c.n_new;
         if (!demod_schedule(st, c.pos, mode, avail, final_flag != 0)) break;
         c.origin_rel = (int)(st.origin - row0);
         asm volatile("" : "+r"(c.origin_rel));  // keep it in a register: ptxas otherwise re-derives it from the constant
@@ -239,6 +243,7 @@ demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         st.freq_offset = c.freq_offset; st.pos = c.pos; st.timing_freq = c.timing_freq;
         st.ph1 = ph1; st.ph2 = ph2; st.p1 = p1; st.p2 = p2;
         dstate[stream] = st;
+        so.n_sym[stream] = st.n_sym;
         unsigned long long dsym = (unsigned long long)(st.n_sym - n_sym0);
         unsigned long long dsmp = (unsigned long long)(st.origin - origin0);
         if (st.flags & kFlagDone) dsmp = (unsigned long long)(avail - origin0);

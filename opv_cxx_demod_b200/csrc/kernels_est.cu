@@ -79,8 +79,9 @@ __global__ void __launch_bounds__(kEstThreads) est_kernel(StreamBuffers sb, Demo
         if (threadIdx.x == 0) dstate[stream].flags |= kFlagEstDone;
         return;
     }
-    const long long row0 = sb.row_base;  // estimate always runs on samples [0, 40000)
-    const uint32_t* row = sb.iq + (long long)stream * sb.stride - row0;
+    // the estimate always runs on samples [0, 40000) before anything has been consumed: in a ring they still sit at
+    // their own offsets (the ring is at least one chunk long)
+    const uint32_t* row = sb.iq + (long long)stream * sb.stride;
     const int n_blocks = (int)(n_use / kSps);
     // role-major: a warp = one role x 32 block slots, so its lanes run the same tile loops (no divergence)
     // and hit 32 different blocks at the same index (stride 45 double2: conflict-free 128-bit loads)

@@ -16,7 +16,7 @@ namespace opvd {
 constexpr int kTrackWarps = 4;
 
 __global__ void __launch_bounds__(32 * kTrackWarps)
-track_kernel(SoftBuffers so, const DemodState* __restrict__ dstate, TrackState* __restrict__ tstate, int n_streams,
+track_kernel(SoftBuffers so, TrackState* __restrict__ tstate, int n_streams,
              FrameRec* __restrict__ frec, int max_frames, TrackEvent* __restrict__ events,
              int32_t* __restrict__ n_events, int max_events, FrameTask* __restrict__ tasks,
              int32_t* __restrict__ n_tasks, int max_tasks, unsigned long long* __restrict__ counters) {
@@ -25,8 +25,23 @@ track_kernel(SoftBuffers so, const DemodState* __restrict__ dstate, TrackState* 
     if (stream >= n_streams) return;
 
     TrackState t = tstate[stream];
-    const long long N = dstate[stream].n_sym;  // soft symbols available
-    const double* soft = so.soft + (long long)stream * so.stride - so.base;
+    const long long N = so.n_sym[stream];  // soft symbols available (this run's snapshot, written by the demodulator)
+    const double* soft_row = so.soft + (long long)stream * so.stride;
+    const long long wrap = so.ring ? so.stride : 0x7fffffffffffffffll;
+    // the 24 soft symbols ending at absolute symbol n, in order (the row may be a ring)
+    auto correlate_at = [&](long long n, double& raw) {
+        long long p = n - (kSyncBits - 1);
+        if (so.ring) p %= so.stride;
+        if (p + kSyncBits <= wrap) return sync_correlate(soft_row + p, raw);
+        double w[kSyncBits];
+#pragma unroll
+        for (int i = 0; i < kSyncBits; ++i) {
+            long long q = p + i;
+            if (q >= wrap) q -= wrap;
+            w[i] = soft_row[q];
+        }
+        return sync_correlate(w, raw);
+    };
     int ne = n_events[stream];
     unsigned long long c_ready = 0, c_acq = 0, c_ok = 0, c_miss = 0, c_lost = 0;
 
@@ -66,7 +81,7 @@ track_kernel(SoftBuffers so, const DemodState* __restrict__ dstate, TrackState* 
                 double raw = 0.0, norm = 0.0;
                 bool hit = false;
                 if (n < N) {
-                    norm = sync_correlate(soft + n - (kSyncBits - 1), raw);
+                    norm = correlate_at(n, raw);
                     hit = hunt_hit(norm, raw);
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -100,7 +115,7 @@ track_kernel(SoftBuffers so, const DemodState* __restrict__ dstate, TrackState* 
             const long long nb = t.anchor + kFrameSymbols;  // :684
             if (nb >= N) break;
             double raw;
-            const double corr = sync_correlate(soft + nb - (kSyncBits - 1), raw);  // lane-uniform
+            const double corr = correlate_at(nb, raw);  // lane-uniform
             if (corr >= 0.70) {  // :688
                 t.misses = 0; t.quality = corr; t.collecting = 1; t.payload_start = nb + 1; t.anchor = nb;
                 push_event(kEvSyncOk, 0, nb, corr, raw);
@@ -130,13 +145,13 @@ track_kernel(SoftBuffers so, const DemodState* __restrict__ dstate, TrackState* 
     }
 }
 
-void launch_track(const SoftBuffers& so, const DemodState* dstate, TrackState* tstate, int n_streams,
+void launch_track(const SoftBuffers& so, TrackState* tstate, int n_streams,
                   FrameRec* frec, int max_frames, TrackEvent* events, int32_t* n_events, int max_events,
                   FrameTask* tasks, int32_t* n_tasks, int max_tasks, unsigned long long* counters,
                   cudaStream_t st) {
     if (n_streams <= 0) return;
     const int grid = (n_streams + kTrackWarps - 1) / kTrackWarps;
-    track_kernel<<<grid, 32 * kTrackWarps, 0, st>>>(so, dstate, tstate, n_streams, frec, max_frames, events,
+    track_kernel<<<grid, 32 * kTrackWarps, 0, st>>>(so, tstate, n_streams, frec, max_frames, events,
                                                     n_events, max_events, tasks, n_tasks, max_tasks, counters);
 }
 

@@ -34,18 +34,64 @@ enum Counter : int {
     kNumCounters = 16
 };
 
+// Per-stream sample rows.  Two layouts:
+//   linear (ring == 0): row[x] holds absolute sample x of the stream (attached captures, batch mode);
+//   ring   (ring == 1): row[x % stride] holds absolute sample x (library-owned buffer in stream mode): the host
+//                       appends behind `avail` and never moves anything; what a launch may still read is
+//                       [origin - 192, avail) of each stream, and the host keeps that span intact (opvd_api.cu).
 struct StreamBuffers {
     const uint32_t* iq;      // packed int16 I/Q, row-major [stream][stride]
-    int64_t stride;          // samples per row (multiple of 4)
-    const int64_t* avail;    // [S] samples valid in each row (absolute sample count since stream start)
-    int64_t row_base;        // absolute sample index held at row offset 0 (multiple of 64; same for all rows)
+    int64_t stride;          // samples per row (multiple of 4; multiple of 64 for a ring)
+    const int64_t* avail;    // [S] absolute sample count pushed so far per stream
+    int32_t ring;
 };
 
+// Soft symbols, same two layouts over absolute symbol indices.
 struct SoftBuffers {
     double* soft;            // [stream][stride]
     int64_t stride;
-    int64_t base;            // absolute symbol index held at row offset 0 (same for all rows)
+    int32_t ring;
+    int64_t* n_sym;          // [S] symbols available after this launch: written by the demodulator, read by the
+                             // tracker (its own array per run in flight, so tile t+1 may be demodulated while
+                             // tile t is still being tracked and decoded)
 };
+
+#if defined(__CUDACC__)
+// One stream's row as seen by one launch: rel = x - base_abs is a small int, the physical offset is
+// base_off + rel, minus the ring length when it wraps (never for a linear row).
+struct RowView {
+    const uint32_t* row;
+    long long base_abs;      // absolute sample index of rel 0 (multiple of 64, <= origin - 128 or 0)
+    int base_off;            // physical offset of rel 0
+    int wrap;                // ring: stride; linear: INT_MAX
+    int rel_end;             // linear: rel values >= rel_end lie beyond the row; ring: INT_MAX
+    __device__ __forceinline__ int phys(int rel) const {
+        int o = base_off + rel;
+        if (o >= wrap) o -= wrap;
+        if (o >= wrap) o -= wrap;
+        return o;
+    }
+};
+__device__ __forceinline__ RowView make_row_view(const StreamBuffers& sb, int stream, long long origin) {
+    RowView v;
+    v.row = sb.iq + (long long)stream * sb.stride;
+    long long b = origin - 128;
+    v.base_abs = b < 0 ? 0 : (b & ~63ll);
+    if (sb.ring) {
+        v.base_off = (int)(v.base_abs % sb.stride);
+        v.wrap = (int)sb.stride;
+        v.rel_end = 0x7fffffff;
+    } else {
+        v.base_off = (int)v.base_abs;
+        v.wrap = 0x7fffffff;
+        const long long e = sb.stride - v.base_abs;
+        v.rel_end = e > 0x7fffffff ? 0x7fffffff : (int)e;
+    }
+    return v;
+}
+// soft-symbol row position of absolute symbol n, and its successor
+__device__ __forceinline__ long long soft_pos(const SoftBuffers& so, long long n) { return so.ring ? n % so.stride : n; }
+#endif
 
 void launch_estimate(const StreamBuffers& sb, DemodState* dstate, double* est_out, int n_streams, int mode,
                      int final_flag, cudaStream_t st);
@@ -87,7 +133,7 @@ cudaError_t launch_demod_coherent(const StreamBuffers& sb, const SoftBuffers& so
                                   int final_flag, double afc_alpha, double pll_bw_hz, unsigned long long* counters,
                                   cudaStream_t st);
 
-void launch_track(const SoftBuffers& so, const DemodState* dstate, TrackState* tstate, int n_streams,
+void launch_track(const SoftBuffers& so, TrackState* tstate, int n_streams,
                   FrameRec* frec, int max_frames, TrackEvent* events, int32_t* n_events, int max_events,
                   FrameTask* tasks, int32_t* n_tasks, int max_tasks, unsigned long long* counters,
                   cudaStream_t st);
