@@ -49,17 +49,22 @@ typedef struct opvd_config {
     int32_t device;            /* CUDA device ordinal, -1 = current device */
     double init_offset_hz;     /* -o <hz> */
     int64_t max_samples;       /* capacity (samples per stream) of the library-owned I/Q buffer used by
-                                  opvd_push_iq*; 0 when captures are attached with opvd_attach_device_iq */
-    int64_t max_symbols;       /* soft-symbol buffer capacity per stream; 0 = derived from max_samples */
-    int32_t max_frames;        /* per-stream frame ring (frames decoded but not yet polled); 0 = derived */
-    int32_t lanes_per_stream;  /* demodulator kernel variant: 0 = chosen from n_streams; 1, 2, 4 = lanes per stream
-                                  of the lane kernels; 32 = one warp per stream (small banks, lowest per-symbol
-                                  latency); 64 = batched, 32 streams per 128-thread CTA (large banks); 128 = pipelined
-                                  batched, 128 streams per 512-thread CTA (experimental) */
+                                  opvd_push_iq*; 0 when captures are attached with opvd_attach_device_iq.  Batch mode: the
+                                  whole capture must fit.  Stream mode: the buffer is a ring (nothing is ever moved); it must
+                                  hold one push plus one chunk (86,720 samples) of carry, and two pushes for a push to
+                                  overlap the kernels of the previous run */
+    int64_t max_symbols;       /* soft-symbol buffer capacity per stream (a ring in stream mode); 0 = derived from
+                                  max_samples */
+    int32_t max_frames;        /* frames per stream that may wait between two polls (the device frame log holds
+                                  n_streams * max_frames entries); 0 = derived */
+    int32_t lanes_per_stream;  /* demodulator kernel variant: 0 = chosen from n_streams; 32 = one warp per stream (small
+                                  banks, lowest per-symbol latency); 96 / 128 = channel-bank kernel, 32 streams per CTA
+                                  with three / four role warps (large banks; 128 is what 0 selects for them) */
     int32_t coherent;          /* -c: CoherentMSKDemodulator (:365-572) instead of MSKDemodulatorAFC; honoured in batch
                                   mode only, like the reference (the streaming branch returns first, :995-1125) */
     int32_t reserved0;
-    double pll_bw_hz;          /* -p <hz>, Costas loop bandwidth (coherent only); <= 0 selects the default 50.0 (:946) */
+    double pll_bw_hz;          /* -p <hz>, Costas loop bandwidth (coherent only), used verbatim like the reference (-p 0
+                                  freezes the loop, :1149); NaN selects the reference's default 50.0 (:946) */
 } opvd_config;
 
 typedef struct opvd_event {
@@ -122,14 +127,20 @@ int opvd_attach_device_iq(opvd_handle* h, const void* d_iq, int64_t stride_sampl
 
 /* ---- processing.  Replaces estimate_offset + demodulate + tracker.process + fdec.decode for all
  * streams (:1030-1065, :1166-1205).  final != 0 is EOF: batch mode runs its single call, stream mode
- * flushes the remainder (:1088-1113).  Work is enqueued on the handle's CUDA stream. */
+ * flushes the remainder (:1088-1113).  Work is only enqueued (estimate + demodulate on one CUDA stream,
+ * tracker + Viterbi on a second one, so they overlap the demodulator of the next run); the call never
+ * waits for the device.  OPVD_ERR_CAPACITY: the run could produce more soft symbols than max_symbols holds. */
 int opvd_run(opvd_handle* h, int final_flag);
 int opvd_sync(opvd_handle* h);
 
 /* ---- output.  Replaces cout.write(frame,134) (:1059-1062, :1200-1203).
- * Returns the number of frames written (<= max_frames), frames with metric >= 0 only, ordered by
- * (stream, frame_idx); each frame is returned once. info may be NULL. */
+ * Waits for the runs enqueued so far, then returns the number of frames written (<= max_frames), frames with
+ * metric >= 0 only; each frame is returned once, in stream order within a poll and in frame order within a
+ * stream.  Only frames decoded since the last poll cross PCIe.  info may be NULL. */
 int opvd_poll_frames(opvd_handle* h, int32_t max_frames, uint8_t* frames134, opvd_frame_info* info);
+/* frames that were overwritten in the device log before anybody polled them (more than n_streams * max_frames
+ * frames between two polls); polling continues with the oldest surviving frame */
+int opvd_frames_lost(opvd_handle* h, uint64_t* out);
 /* events of one stream not yet returned (the tracker's stderr lines) */
 int opvd_poll_events(opvd_handle* h, int32_t stream, int32_t max_events, opvd_event* out);
 /* soft symbols [first_sym, first_sym+n) of one stream (parity/debug; the reference never exposes them) */
@@ -139,8 +150,11 @@ int opvd_get_stream_info(opvd_handle* h, int32_t stream, opvd_stream_info* out);
 int opvd_get_counters(opvd_handle* h, uint64_t* out, int32_t n);
 /* device pointer of the same counters (uint64[OPVD_NUM_COUNTERS]) for an in-place ncclAllReduce */
 int opvd_counters_device_ptr(opvd_handle* h, void** out);
-/* elapsed GPU time of the last opvd_run, measured with CUDA events on the handle's stream:
- * ms[0]=estimate, ms[1]=demod, ms[2]=track, ms[3]=decode, ms[4]=total */
+/* GPU time since the last opvd_create / opvd_reset, measured with CUDA events on the handle's streams:
+ * ms[0..3] = summed kernel times of the estimate, demodulator, tracker and decoder launches of every run,
+ * ms[4] = elapsed time from the start of the first run to the end of the last one (with several runs in flight
+ * the tracker + decoder of run t overlap the demodulator of run t+1, so ms[4] < ms[0]+..+ms[3]).  Waits for the
+ * enqueued runs. */
 int opvd_last_run_ms(opvd_handle* h, float* ms5);
 /* the demodulator kernel variant in use (opvd_config.lanes_per_stream with 0 resolved) */
 int opvd_demod_lanes(opvd_handle* h);

@@ -22,7 +22,8 @@
 // offset, so z_t^k = tau^(+/-k) * zeta^k: one squaring chain of zeta serves both tones, tau^10, tau^20 are
 // constants, and tau^40 = j exactly (z_1^40 = j*zeta^40, z_2^40 = -j*zeta^40).
 #pragma once
-#include "demod_batch_core.cuh"
+#include "demod_core.cuh"
+#include "fastmath.cuh"
 
 namespace opvd {
 
@@ -36,6 +37,9 @@ static __constant__ BankConsts g_bk = OPVD_BANK_CONSTS_INIT;
 #else
 static const BankConsts g_bk = OPVD_BANK_CONSTS_INIT;
 #endif
+
+OPVD_HD double clamp_sym_b(double v, double lim) { return fabs(v) > lim ? copysign(lim, v) : v; }
+OPVD_HD_COLD double batch_afc_corner(cplx dom, cplx prev, double ph) { return afc_phase_signed_zero(dom, prev, ph); }
 
 // a = (c + js) * v,  b = (c - js) * v   (6 operations for both)
 OPVD_HD void tone_pair(double c, double s, cplx v, cplx& a, cplx& b) {
@@ -216,6 +220,86 @@ OPVD_HD void bank_afc(BankAfc& r, cplx O1, cplx O2, bool tone1, cplx zeta40, dou
     const double a1 = fma(40.0, inc1, r.ph1), a2 = fma(40.0, inc2, r.ph2);  // :250-262
     r.ph1 = fma(-K.two_pi, rint(a1 * K.inv_two_pi), a1);
     r.ph2 = fma(-K.two_pi, rint(a2 * K.inv_two_pi), a2);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same window work cut in two halves for the four-warp kernel (two window warps per 32 streams):
+//   LO warp: blocks H1, H2 (slots 10..29) -> P_t;  on-time combination, soft decision, dominant tone; H0 -> early gate
+//   HI warp: blocks H3, H4 (slots 30..49) -> R_t;  H5 of both tones (no need to wait for the decision) -> late gate
+// Every value is computed by exactly the operations of bank_on_blocks / bank_on_time / bank_early_late above, so
+// the two kernels produce identical bits.
+
+// two adjacent 10-slot blocks starting at slot k0, both tones; fA/fB = first raw sample of each block
+template <class Win>
+OPVD_HD void bank_two_blocks(Win win, int k0, cplx z1, cplx z2, cplx (&A)[2], cplx (&B)[2], cplx& fA, cplx& fB) {
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        double I, Q;
+        win(k0 + 10 * m + 9, I, Q);
+        A[m] = {I, Q};
+        B[m] = {I, Q};
+    }
+#pragma unroll
+    for (int j = 8; j >= 0; --j) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            double I, Q;
+            win(k0 + 10 * m + j, I, Q);
+            hstep(A[m], z1, I, Q);
+            hstep(B[m], z2, I, Q);
+            if (j == 0 && m == 0) fA = {I, Q};
+            if (j == 0 && m == 1) fB = {I, Q};
+        }
+    }
+}
+// one 10-slot block starting at slot k0, both tones
+template <class Win>
+OPVD_HD void bank_block_both(Win win, int k0, cplx z1, cplx z2, cplx& H1, cplx& H2) {
+    double I, Q;
+    win(k0 + 9, I, Q);
+    H1 = {I, Q};
+    H2 = {I, Q};
+#pragma unroll
+    for (int j = 8; j >= 0; --j) {
+        win(k0 + j, I, Q);
+        hstep(H1, z1, I, Q);
+        hstep(H2, z2, I, Q);
+    }
+}
+// one 10-slot block starting at slot k0, one tone; f0 = its first raw sample
+template <class Win>
+OPVD_HD void bank_block_one(Win win, int k0, cplx z, cplx& H, cplx& f0) {
+    double I, Q;
+    win(k0 + 9, I, Q);
+    H = {I, Q};
+#pragma unroll
+    for (int j = 8; j >= 0; --j) {
+        win(k0 + j, I, Q);
+        hstep(H, z, I, Q);
+        if (j == 0) f0 = {I, Q};
+    }
+}
+// LO warp: on-time correlations from its own P_t and the HI warp's R_t
+OPVD_HD void bank_on_time_from_halves(double f, const BankLo& lo, const BankPow& pw, cplx P1, cplx P2, cplx R1, cplx R2, cplx s10,
+                                      cplx s50, cplx& O1, cplx& O2, double& eO1, double& eO2) {
+    const cplx X1 = cfma(pw.qq1, R1, P1), X2 = cfma(pw.qq2, R2, P2);
+    cplx g1, h1, g2, h2;
+    interp_weights(lo.z1, f, g1, h1);
+    interp_weights(lo.z2, f, g2, h2);
+    O1 = bank_interp(g1, h1, X1, s50, s10, bank_z40(pw.zeta40, 0));
+    O2 = bank_interp(g2, h2, X2, s50, s10, bank_z40(pw.zeta40, 1));
+    eO1 = cnorm(O1);
+    eO2 = cnorm(O2);
+}
+// interpolated gate energy of  G = a + q*(b + qq*c)  (early: a = H0, b = P, c = H3; late: a = H2, b = R, c = H5)
+OPVD_HD double bank_gate_energy(double f, cplx z, cplx q, cplx qq, cplx z40, cplx a, cplx b, cplx c, cplx last, cplx first,
+                                cplx fix) {
+    const cplx G = cfma(q, cfma(qq, c, b), a);
+    cplx g, h;
+    interp_weights(z, f, g, h);
+    cplx Gi = bank_interp(g, h, G, last, first, z40);
+    Gi.r -= fix.r; Gi.i -= fix.i;
+    return cnorm(Gi);
 }
 
 }  // namespace opvd

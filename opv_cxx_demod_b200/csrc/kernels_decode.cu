@@ -72,8 +72,16 @@ __device__ __forceinline__ int deinterleave_inv(int j) {
     return (pos % 67) * 32 + pos / 67;
 }
 
-__device__ __forceinline__ void decode_one(const double* __restrict__ soft, unsigned char* wsm, const uint2* bm_tbl,
-                                           uint8_t* out_frame, int32_t* out_metric, unsigned long long* counters) {
+// soft: start of the stream's soft row, p0: row position of the first payload symbol, wrap: ring length of the row
+// (a payload of 2144 symbols may wrap once; 2^62 for a linear row)
+__device__ __forceinline__ void decode_one(const double* __restrict__ soft_row, long long p0, long long wrap, unsigned char* wsm,
+                                           const uint2* bm_tbl, uint8_t* out_frame, int32_t* out_metric,
+                                           unsigned long long* counters) {
+    auto soft_at = [&](int j) {
+        long long q = p0 + j;
+        if (q >= wrap) q -= wrap;
+        return soft_row[q];
+    };
     const int lane = threadIdx.x & 31;
     double* dsum = reinterpret_cast<double*>(wsm);
     uint32_t* dec = reinterpret_cast<uint32_t*>(wsm);
@@ -83,8 +91,7 @@ __device__ __forceinline__ void decode_one(const double* __restrict__ soft, unsi
     // ---- scale = mean |soft| with the reference's sequential summation order (:856-858)
     double scale = 0.0;
     for (int half = 0; half < 2; ++half) {
-        const double* src = soft + half * (kEncodedBits / 2);
-        for (int i = lane; i < kEncodedBits / 2; i += 32) dsum[i] = fabs(src[i]);
+        for (int i = lane; i < kEncodedBits / 2; i += 32) dsum[i] = fabs(soft_at(half * (kEncodedBits / 2) + i));
         __syncwarp();
 #pragma unroll 8
         for (int i = 0; i < kEncodedBits / 2; ++i) scale += dsum[i];  // lane-uniform broadcast reads
@@ -101,7 +108,7 @@ __device__ __forceinline__ void decode_one(const double* __restrict__ soft, unsi
     }
     // ---- quantise (:863-866) and scatter to deinterleaved order (:869-871)
     for (int j = lane; j < kEncodedBits; j += 32) {
-        const double n = __dadd_rn(__dmul_rn(__ddiv_rn(-soft[j], scale), 3.5), 3.5);
+        const double n = __dadd_rn(__dmul_rn(__ddiv_rn(-soft_at(j), scale), 3.5), 3.5);
         int v = (int)__dadd_rn(n, 0.5);  // C truncation toward zero
         v = v < 0 ? 0 : (v > 7 ? 7 : v);
         q[deinterleave_inv(j)] = (uint8_t)v;
@@ -189,21 +196,45 @@ __device__ __forceinline__ void decode_one(const double* __restrict__ soft, unsi
 __global__ void __launch_bounds__(32 * kDecWarps)
 decode_tasks_kernel(SoftBuffers so, const FrameTask* __restrict__ tasks, const int32_t* __restrict__ n_tasks_dev,
                     int max_tasks, uint8_t* __restrict__ frames, int32_t* __restrict__ metrics, int max_frames,
-                    unsigned long long* __restrict__ counters) {
+                    const FrameRec* __restrict__ frec, FrameLogEntry* __restrict__ log, const unsigned long long* log_count,
+                    long long log_cap, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char dsm[];
-    const int warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int n = *n_tasks_dev;
     if (n > max_tasks) n = max_tasks;
+    const unsigned long long log_base = *log_count;  // frames logged by earlier runs (advanced after this kernel)
     uint2* bm_tbl = reinterpret_cast<uint2*>(dsm);
     build_bm_table(bm_tbl);
     unsigned char* wsm = dsm + kBmTableBytes + (size_t)warp * kDecSmemPerWarp;
+    const long long wrap = so.ring ? so.stride : (1ll << 62);
     for (int task = blockIdx.x * kDecWarps + warp; task < n; task += gridDim.x * kDecWarps) {
         const FrameTask ft = tasks[task];
-        const double* soft = so.soft + (long long)ft.stream * so.stride - so.base + ft.payload_start;
+        const double* soft_row = so.soft + (long long)ft.stream * so.stride;
         const long long o = (long long)ft.stream * max_frames + (ft.slot % max_frames);
-        decode_one(soft, wsm, bm_tbl, frames + o * kFrameBytes, metrics + o, counters);
+        decode_one(soft_row, so.ring ? ft.payload_start % so.stride : ft.payload_start, wrap, wsm, bm_tbl,
+                   frames + o * kFrameBytes, metrics + o, counters);
+        __syncwarp();
+        // ---- the same frame into the contiguous log the host polls (new entries only cross PCIe)
+        FrameLogEntry* e = log + (long long)((log_base + (unsigned long long)task) % (unsigned long long)log_cap);
+        const uint8_t* outb = wsm + kDecBytesPerWarp;  // decode_one leaves the 134 bytes here (zeros when dropped)
+        int metric = 0;
+        if (lane == 0) {
+            metric = metrics[o];  // written by this lane in decode_one
+            e->stream = ft.stream; e->frame_idx = ft.slot; e->metric = metric; e->reserved = 0;
+            e->payload_start = ft.payload_start; e->ready_idx = frec[o].ready_idx; e->quality = frec[o].quality;
+        }
+        metric = __shfl_sync(0xffffffffu, metric, 0);
+        if (metric >= 0)
+            for (int i = lane; i < kFrameBytes; i += 32) e->frame[i] = outb[i];
         __syncwarp();
     }
+}
+
+// after the decoder: the frames of this run become visible to the host's poll
+__global__ void log_advance_kernel(unsigned long long* log_count, const int32_t* n_tasks_dev, int max_tasks) {
+    int n = *n_tasks_dev;
+    if (n > max_tasks) n = max_tasks;
+    *log_count += (unsigned long long)n;
 }
 
 __global__ void __launch_bounds__(32 * kDecWarps)
@@ -215,8 +246,8 @@ decode_payloads_kernel(const double* __restrict__ payloads, int n, uint8_t* __re
     build_bm_table(bm_tbl);
     unsigned char* wsm = dsm + kBmTableBytes + (size_t)warp * kDecSmemPerWarp;
     for (int task = blockIdx.x * kDecWarps + warp; task < n; task += gridDim.x * kDecWarps) {
-        decode_one(payloads + (long long)task * kEncodedBits, wsm, bm_tbl, frames + (long long)task * kFrameBytes,
-                   metrics + task, counters);
+        decode_one(payloads + (long long)task * kEncodedBits, 0, 1ll << 62, wsm, bm_tbl,
+                   frames + (long long)task * kFrameBytes, metrics + task, counters);
         __syncwarp();
     }
 }
@@ -232,31 +263,23 @@ static int decode_grid(int n_tasks) {
 }
 
 void launch_decode(const SoftBuffers& so, const FrameTask* tasks, const int32_t* n_tasks_dev, int n_tasks_host,
-                   uint8_t* frames, int32_t* metrics, int max_frames, unsigned long long* counters,
-                   cudaStream_t st) {
+                   uint8_t* frames, int32_t* metrics, int max_frames, const FrameRec* frec, FrameLogEntry* log,
+                   unsigned long long* log_count, long long log_cap, unsigned long long* counters, cudaStream_t st) {
     // n_tasks_host is an upper bound used only to size the grid; the kernel reads the exact count on device
     if (n_tasks_host <= 0) return;
     const size_t smem = (size_t)kBmTableBytes + (size_t)kDecWarps * kDecSmemPerWarp;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(decode_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(decode_payloads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
+    cudaFuncSetAttribute(decode_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device
     decode_tasks_kernel<<<decode_grid(n_tasks_host), 32 * kDecWarps, smem, st>>>(so, tasks, n_tasks_dev, n_tasks_host,
-                                                                              frames, metrics, max_frames, counters);
+                                                                              frames, metrics, max_frames, frec, log,
+                                                                              log_count, log_cap, counters);
+    log_advance_kernel<<<1, 1, 0, st>>>(log_count, n_tasks_dev, n_tasks_host);
 }
 
 void launch_decode_payloads(const double* payloads, int n, uint8_t* frames, int32_t* metrics,
                             unsigned long long* counters, cudaStream_t st) {
     if (n <= 0) return;
     const size_t smem = (size_t)kBmTableBytes + (size_t)kDecWarps * kDecSmemPerWarp;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(decode_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(decode_payloads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
+    cudaFuncSetAttribute(decode_payloads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device
     decode_payloads_kernel<<<decode_grid(n), 32 * kDecWarps, smem, st>>>(payloads, n, frames, metrics, counters);
 }
 

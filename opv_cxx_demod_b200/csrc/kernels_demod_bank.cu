@@ -1,25 +1,25 @@
 // kernels_demod_bank.cu — A1/A3/A4 for sm_100a, CHANNEL-BANK variant (demod_bank_core.cuh): the kernel for
 // thousands of streams (north-star regime, >= 16,384 streams per GPU = 128 per SM).
 //
-// A CTA of 96 threads owns 32 streams; lane = stream in each of its three warps, so every instruction does 32
-// streams' worth of work and nothing is ever exchanged inside a warp.  The warps are three free-running roles
-// coupled only by named barriers (producer/consumer hand-offs through shared memory), never by a CTA barrier:
-//   warp 0  WINDOW  on-time Horner sums of both tones -> soft symbol + dominant tone -> hands the on-time
-//                   correlations to the AFC warp -> early/late sums of the dominant tone only -> TED, timing
-//                   loop, next position, call schedule (:221-286, :313, :1012-1113)
-//   warp 1  AFC     phase detector, AFC loop, LO steps z (handed back first: the next symbol's Horner needs
-//                   nothing else), then the LO powers z^10, z^20, zeta^40 for the gate combination (:289-310)
-//   warp 2  STAGE   moves the streams' samples from HBM into the transposed shared-memory ring, two batches of
-//                   5 x 32 bytes per lane in flight, 2-4 symbols ahead of the window (flow control through two
-//                   per-stream words in shared memory, no barrier)
-// The AFC chain of symbol n therefore overlaps the early/late + timing half of symbol n on the same SM
-// sub-partition, and the FP64 pipe — the unit that bounds this kernel — sees two independent instruction
-// streams per 32 streams instead of one alternating window/loop phase (round 1: 47 % busy).
+// A CTA owns 32 streams; lane = stream in every warp, so every instruction does 32 streams' worth of work and
+// nothing is ever exchanged inside a warp.  The warps are free-running ROLES coupled only by named barriers
+// (producer/consumer hand-offs through shared memory), never by a CTA barrier:
+//   WINDOW  Horner block sums -> gate combination -> soft symbol, dominant tone -> early/late gates of the
+//           dominant tone only -> TED, timing loop, next position, call schedule (:221-286, :313, :1012-1113).
+//           In the four-warp kernel the window is cut in two halves that run as two warps (LO: blocks H1, H2, H0,
+//           on-time combination, early gate, timing loop; HI: blocks H3, H4, H5, late gate): one warp per SM
+//           sub-partition cannot hide its own issue latencies (measured: 2.9 cycles per instruction, FP64 pipe
+//           46 % busy with the single window warp of the three-warp kernel, profiles/ncu_bank_r02_a_roles.txt).
+//   AFC     phase detector, AFC loop, LO steps z (handed back first: the next symbol's Horner needs nothing else),
+//           then the LO powers z^10, z^20, zeta^40 for the gate combination (:289-310)
+//   STAGE   moves the streams' samples from HBM into the transposed shared-memory ring, two batches of 32-byte
+//           sectors per lane in flight, 2-4 symbols ahead of the window (flow control through two per-stream words
+//           in shared memory, no barrier)
+// The AFC chain of symbol n overlaps the early/late + timing part of symbol n, and the FP64 pipe — the unit that
+// bounds this kernel — always sees several independent instruction streams.
 //
 // Sample ring: ring[row][stream], row = sample index mod 256, rows 0..63 mirrored behind row 255 so a 61-row
 // window never wraps; lane s always reads bank s (conflict-free whatever the streams' window positions are).
-// Words are stored with Q's sign bit flipped (offset binary) so Q converts with one integer op + one DADD and I
-// with one I2F.F64.S16 (XU pipe).
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdlib>
@@ -33,17 +33,15 @@ namespace opvd {
 namespace {
 
 constexpr int kSpc = 32;             // streams per CTA
-constexpr int kThreads = 96;         // window, AFC, staging warp
 constexpr int kRingRows = 256;       // samples per stream resident in shared memory (power of two)
 constexpr int kMirrorRows = 64;      // rows 0..63 repeated after row 255
 constexpr int kRows = kRingRows + kMirrorRows;
 constexpr int kChunk = 8;            // samples per 32-byte sector
-constexpr int kBatchChunks = 5;      // chunks per staging batch: 40 samples = one symbol's worth
-constexpr int kBatch = kChunk * kBatchChunks;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kQBias = 0x80000000u;
 
-enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3 };  // named barriers (0 is __syncthreads)
+// named barriers (0 is __syncthreads)
+enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3, kBarX1 = 4, kBarX2 = 5, kBarX3 = 6, kBarX4 = 7 };
 enum : int { kFlagTone1 = 1, kFlagFirst = 2, kFlagLive = 4, kFlagExit = 8 };
 
 struct __align__(16) BankSmem {
@@ -51,33 +49,46 @@ struct __align__(16) BankSmem {
     double o[4][kSpc];            // WINDOW -> AFC: O1.r, O1.i, O2.r, O2.i
     double z[4][kSpc];            // AFC -> WINDOW: z1.r, z1.i, z2.r, z2.i
     double pw[10][kSpc];          // AFC -> WINDOW: q1, q2, qq1, qq2, zeta40
+    double x1[12][kSpc];          // HI -> LO: R1, R2, H3 (F1), H3 (F2), s40, s50
+    double x2[4][kSpc];           // LO -> HI: H2 of the dominant tone, s20
+    double x3[kSpc];              // HI -> LO: late-gate energy
+    double x4f[kSpc];             // LO -> HI: interpolation fraction of the next symbol
+    int x4w[kSpc];                // LO -> HI: window start of the next symbol
+    int x4flags[kSpc];            // LO -> HI: kFlagLive / kFlagExit for the next symbol
+    int x2flags[kSpc];            // LO -> HI: kFlagTone1
     int flags[kSpc];              // WINDOW -> AFC: kFlag*
     int w0[kSpc];                 // WINDOW -> STAGE: row-relative sample index of window slot 0 of the current symbol
     int fill[kSpc];               // STAGE -> WINDOW: samples [.., fill) of the stream's row are in the ring
     int live[kSpc];               // WINDOW -> STAGE: stream still has symbols to demodulate in this launch
     int exit_flag;                // WINDOW -> STAGE
+    int rot;                      // role rotation of this CTA (four-warp kernel)
 };
 
-template <int ID>
-__device__ __forceinline__ void bar_sync() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
-template <int ID>
-__device__ __forceinline__ void bar_arrive() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
+template <int ID, int N>
+__device__ __forceinline__ void bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+template <int ID, int N>
+__device__ __forceinline__ void bar_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
 __device__ __forceinline__ int ld_vol(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 __device__ __forceinline__ void st_vol(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
 
-// ring word (I raw, Q offset-binary) -> doubles.  I always converts with one I2F.F64.S16 (XU pipe, 8 cycles per warp
-// instruction, one issue slot); Q either the same way (after undoing the offset) or with the 2^52 bias trick (two
-// integer-pipe instructions + one DADD on the FP64 pipe).  QX picks the split by window slot: the kernel is bound by
-// issue slots, the FP64 pipe and the XU pipe at nearly the same level, so the split balances the three.
-//   QX = 0  every Q through the bias trick      QX = 1  odd slots through XU      QX = 2  every Q through XU
+// Ring word -> doubles.  I always converts with one I2F.F64.S16 (XU pipe: 8 cycles per warp instruction, one issue
+// slot).  Q depends on the storage format, chosen by QX for the whole kernel:
+//   QX = 0  Q stored offset-binary; 2^52 bias trick (two integer-pipe instructions + one DADD on the FP64 pipe)
+//   QX = 1  Q stored offset-binary; odd window slots through XU (after undoing the offset), even slots bias trick
+//   QX = 2  Q stored raw; one I2F.F64.S16 on the upper half (every conversion on the XU pipe)
+// The kernel is bound by issue slots, the FP64 pipe and the XU pipe at nearly the same level; QX balances them.
 template <int QX>
 __device__ __forceinline__ void unpack_ring(uint32_t w, int k, double& I, double& Q) {
     I = (double)(int16_t)(w & 0xFFFFu);
-    if (QX == 2 || (QX == 1 && (k & 1)))
+    if (QX == 2)
+        Q = (double)(int16_t)(w >> 16);
+    else if (QX == 1 && (k & 1))
         Q = (double)(int16_t)((w >> 16) ^ 0x8000u);
     else
         Q = __hiloint2double(0x43300000, (int)(w >> 16)) - 4503599627403264.0;  // 2^52 + 2^15
 }
+template <int QX>
+__device__ __forceinline__ uint32_t ring_word(uint32_t raw) { return QX == 2 ? raw : raw ^ kQBias; }
 
 __device__ __forceinline__ void ldg256(const uint32_t* p, uint4& a, uint4& b) {  // read-once, 32-byte aligned
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -109,10 +120,11 @@ __device__ __forceinline__ void chunk_load(const RowView& v, int rel, bool wide,
         b = make_uint4(0u, 0u, 0u, 0u);
     }
 }
+template <int QX>
 __device__ __forceinline__ void chunk_store(BankSmem& sm, int s, int idx, uint4 a, uint4 b) {
     const int r = idx & (kRingRows - 1);
-    const uint32_t w[8] = {a.x ^ kQBias, a.y ^ kQBias, a.z ^ kQBias, a.w ^ kQBias,
-                           b.x ^ kQBias, b.y ^ kQBias, b.z ^ kQBias, b.w ^ kQBias};
+    const uint32_t w[8] = {ring_word<QX>(a.x), ring_word<QX>(a.y), ring_word<QX>(a.z), ring_word<QX>(a.w),
+                           ring_word<QX>(b.x), ring_word<QX>(b.y), ring_word<QX>(b.z), ring_word<QX>(b.w)};
 #pragma unroll
     for (int j = 0; j < 8; ++j) sm.ring[r + j][s] = w[j];
     if (r < kMirrorRows) {
@@ -122,8 +134,9 @@ __device__ __forceinline__ void chunk_store(BankSmem& sm, int s, int idx, uint4 
 }
 
 // early-gate correction for the first symbol of a call (rare: kept out of line)
+template <int QX>
 __device__ __noinline__ cplx first_fix_cold(const uint32_t* win, double f, cplx z) {
-    return first_symbol_fix_w([&](int kk) { return win[kk * kSpc] ^ kQBias; }, f, z);
+    return first_symbol_fix_w([&](int kk) { return ring_word<QX>(win[kk * kSpc]); }, f, z);
 }
 // call scheduling out of line; everything it touches by reference lives in local memory
 __device__ __noinline__ bool schedule_cold(DemodState& st, int mode, long long avail, bool final_flag) {
@@ -133,10 +146,208 @@ __device__ __noinline__ bool schedule_cold(DemodState& st, int mode, long long a
     return live;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Per-stream bookkeeping of the window role that owns the timing loop and the call schedule.
+// The DemodState record itself stays OUTSIDE this struct: its address escapes to the out-of-line scheduler, and an
+// object that shares a struct with an address-taken member lands in local memory as a whole.
+struct WindowCtl {
+    long long avail, n_sym0, origin0, base_abs;
+    double* soft_row;
+    int soft_wrap, soft_idx, n_new;
+    double timing_freq, pos, call_len_d, f;
+    int sym_in_call, origin_rel, w0;
+    bool live;
+
+    __device__ __forceinline__ void init(DemodState& st, const StreamBuffers& sb, const SoftBuffers& so, int stream,
+                                         bool valid, int mode, int final_flag) {
+        avail = sb.avail[stream];
+        soft_row = so.soft + (long long)stream * so.stride;
+        soft_wrap = so.ring ? (int)so.stride : 0x7fffffff;
+        soft_idx = (int)soft_pos(so, st.n_sym);  // row position of the next soft symbol
+        n_new = 0;                               // symbols produced by this launch
+        n_sym0 = st.n_sym; origin0 = st.origin;
+        base_abs = make_row_view(sb, stream, st.origin).base_abs;
+        timing_freq = st.timing_freq;
+        live = valid && schedule_cold(st, mode, avail, final_flag != 0);
+        pos = st.pos;
+        sym_in_call = st.sym_in_call;
+        call_len_d = (double)st.call_len;
+        origin_rel = (int)(st.origin - base_abs);
+        w0 = 0; f = 0.0;
+        if (live) locate();
+    }
+    __device__ __forceinline__ void locate() {
+        const int b = __double2int_rz(pos);  // pos >= 0: truncation == floor (:125)
+        f = pos - (double)b;
+        w0 = origin_rel + b - kWinLead;
+    }
+    __device__ __forceinline__ void put_soft(double v) {
+        soft_row[soft_idx] = v;  // :268
+        if (++soft_idx == soft_wrap) soft_idx = 0;
+        ++n_new;
+    }
+    // after the timing loop has advanced pos: next symbol of this stream, maybe through a call boundary
+    __device__ __forceinline__ void advance(DemodState& st, int mode, int final_flag) {
+        sym_in_call = 1;  // any non-zero value: the open call has produced symbols
+        if (!((pos + 40.0) + 10.0 < call_len_d)) {  // :221 fails: close the call, maybe open the next
+            st.n_sym = n_sym0 + n_new;
+            st.sym_in_call = sym_in_call;
+            st.pos = pos;
+            live = schedule_cold(st, mode, avail, final_flag != 0);
+            pos = st.pos;
+            sym_in_call = st.sym_in_call;
+            call_len_d = (double)st.call_len;
+            origin_rel = (int)(st.origin - base_abs);
+        }
+        if (live) locate();
+    }
+    // persist: this role writes its fields of the record, the AFC warp patches its own afterwards
+    __device__ __forceinline__ void persist(DemodState& st, const SoftBuffers& so, DemodState* dstate, int stream,
+                                            unsigned long long* counters) {
+        st.n_sym = n_sym0 + n_new;
+        so.n_sym[stream] = st.n_sym;
+        DemodState* d = dstate + stream;
+        d->pos = pos; d->timing_freq = timing_freq; d->origin = st.origin; d->call_len = st.call_len;
+        d->n_sym = st.n_sym; d->sym_in_call = sym_in_call; d->flags = st.flags;
+        unsigned long long dsym = (unsigned long long)n_new;
+        unsigned long long dsmp = (unsigned long long)(st.origin - origin0);
+        if (st.flags & kFlagDone) dsmp = (unsigned long long)(avail - origin0);
+        if (dsym) atomicAdd(&counters[kCtrSymbols], dsym);
+        if (dsmp) atomicAdd(&counters[kCtrSamples], dsmp);
+    }
+};
+
+__device__ __forceinline__ void wait_window(BankSmem& sm, int s, bool live, int w0) {
+    // normally true at once: the staging warp runs 2-4 symbols ahead
+    while (!__all_sync(kFull, !live || ld_vol(&sm.fill[s]) >= w0 + kWin)) {}
+    __threadfence_block();
+}
+__device__ __forceinline__ void load_lo(const BankSmem& sm, int s, BankLo& lo) {
+    lo.z1 = {sm.z[0][s], sm.z[1][s]};
+    lo.z2 = {sm.z[2][s], sm.z[3][s]};
+    lo.inc1 = 0.0; lo.inc2 = 0.0;
+}
+__device__ __forceinline__ void load_pow(const BankSmem& sm, int s, BankPow& pw) {
+    pw.q1 = {sm.pw[0][s], sm.pw[1][s]};
+    pw.q2 = {sm.pw[2][s], sm.pw[3][s]};
+    pw.qq1 = {sm.pw[4][s], sm.pw[5][s]};
+    pw.qq2 = {sm.pw[6][s], sm.pw[7][s]};
+    pw.zeta40 = {sm.pw[8][s], sm.pw[9][s]};
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// AFC role.  NW = threads taking part in the z / power hand-offs (64: one window warp, 96: two).
+template <int NW>
+__device__ __forceinline__ void role_afc(BankSmem& sm, int s, int stream, bool valid, DemodState* dstate, double afc_alpha) {
+    const DemodState* d0 = dstate + stream;
+    BankAfc afc = {d0->freq_offset, d0->ph1, d0->ph2, d0->p1, d0->p2};
+    BankLo lo;
+    BankPow pw;
+    {
+        double d;
+        const cplx zeta = bank_zeta_general(afc.freq_offset, d);  // a -o offset may exceed the fast range
+        bank_lo_from_zeta(zeta, d, lo, g_fm);
+        bank_pow_from_zeta(zeta, pw, g_bk);
+    }
+    __syncthreads();  // (1)
+    auto publish_z = [&]() {
+        sm.z[0][s] = lo.z1.r; sm.z[1][s] = lo.z1.i; sm.z[2][s] = lo.z2.r; sm.z[3][s] = lo.z2.i;
+        bar_arrive<kBarZ, NW>();
+    };
+    auto publish_pow = [&]() {
+        sm.pw[0][s] = pw.q1.r; sm.pw[1][s] = pw.q1.i; sm.pw[2][s] = pw.q2.r; sm.pw[3][s] = pw.q2.i;
+        sm.pw[4][s] = pw.qq1.r; sm.pw[5][s] = pw.qq1.i; sm.pw[6][s] = pw.qq2.r; sm.pw[7][s] = pw.qq2.i;
+        sm.pw[8][s] = pw.zeta40.r; sm.pw[9][s] = pw.zeta40.i;
+        bar_arrive<kBarPow, NW>();
+    };
+    publish_z();
+    publish_pow();
+    for (;;) {
+        bar_sync<kBarO, 64>();
+        const int fl = sm.flags[s];
+        if (fl & kFlagExit) break;  // warp-uniform: the window warp sets it on every lane
+        const cplx O1 = {sm.o[0][s], sm.o[1][s]}, O2 = {sm.o[2][s], sm.o[3][s]};
+        // no AFC update on the first symbol of a call (:289): same LO steps next symbol
+        const bool update = (fl & kFlagLive) && !(fl & kFlagFirst);
+        cplx zeta = {1.0, 0.0};
+        if (fl & kFlagLive) {
+            bank_afc(afc, O1, O2, (fl & kFlagTone1) != 0, pw.zeta40, lo.inc1, lo.inc2, (fl & kFlagFirst) != 0, afc_alpha,
+                     g_fm);
+            if (update) {
+                double d;
+                zeta = bank_zeta_fast(afc.freq_offset, d, g_fm);  // |offset| <= 2 kHz after the clamp (:303)
+                bank_lo_from_zeta(zeta, d, lo, g_fm);
+            }
+        }
+        publish_z();  // z goes out first: the next symbol's Horner needs nothing else
+        if (update) bank_pow_from_zeta(zeta, pw, g_bk);
+        publish_pow();
+    }
+    __syncthreads();  // (2) the window warp has written the records
+    if (valid) {
+        DemodState* d = dstate + stream;
+        d->freq_offset = afc.freq_offset; d->ph1 = afc.ph1; d->ph2 = afc.ph2; d->p1 = afc.p1; d->p2 = afc.p2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// STAGE role.  NB chunks (32-byte sectors) per batch and lane, two batches in flight.
+template <int QX, int NB>
+__device__ __forceinline__ void role_stage(BankSmem& sm, int s, int stream, const StreamBuffers& sb, const DemodState* dstate) {
+    constexpr int kBatch = kChunk * NB;
+    const RowView view = make_row_view(sb, stream, dstate[stream].origin);  // same base as the window warp
+    const bool wide = ((reinterpret_cast<uintptr_t>(sb.iq) | (uintptr_t)(sb.stride * 4)) & 31u) == 0;
+    sm.fill[s] = -(1 << 30);
+    __syncthreads();  // (1)
+    int req;  // samples [.., req) of this lane's row have been requested (multiple of 8)
+    {
+        const int w0 = sm.w0[s];
+        req = (w0 < 0 ? 0 : w0) & ~(kChunk - 1);
+    }
+    uint4 bufA[2 * NB], bufB[2 * NB];
+    int idxA = -1, idxB = -1;  // row index of the batch held in the buffer (-1: empty)
+    auto request = [&](uint4 (&buf)[2 * NB], int& idx) {
+        const int w0 = ld_vol(&sm.w0[s]);
+        const bool can = ld_vol(&sm.live[s]) != 0 && req + kBatch <= w0 + kRingRows - kChunk && req < view.rel_end;
+        idx = -1;
+        if (can) {
+#pragma unroll
+            for (int c = 0; c < NB; ++c) chunk_load(view, req + kChunk * c, wide, buf[2 * c], buf[2 * c + 1]);
+            idx = req;
+            req += kBatch;
+        }
+        return can;
+    };
+    auto retire = [&](uint4 (&buf)[2 * NB], int& idx) {
+        const bool had = idx >= 0;
+        if (had) {
+#pragma unroll
+            for (int c = 0; c < NB; ++c) chunk_store<QX>(sm, s, idx + kChunk * c, buf[2 * c], buf[2 * c + 1]);
+            __threadfence_block();
+            st_vol(&sm.fill[s], idx + kBatch);
+            idx = -1;
+        }
+        return had;
+    };
+    for (;;) {
+        bool work = request(bufA, idxA);
+        work |= retire(bufB, idxB);
+        work |= request(bufB, idxB);
+        work |= retire(bufA, idxA);
+        if (!__any_sync(kFull, work)) {
+            if (ld_vol(&sm.exit_flag)) break;
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();  // (2)
+}
+
 }  // namespace
 
+// =================================================================================================================
+// Three-warp kernel: WINDOW, AFC, STAGE (96 threads)
 template <int QX>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(96, 4)
 demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
                   int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -146,220 +357,203 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     const bool valid = stream_raw < n_streams;
     const int stream = valid ? stream_raw : n_streams - 1;
 
+    if (role == 1) { role_afc<64>(sm, s, stream, valid, dstate, afc_alpha); return; }
+    if (role == 2) { role_stage<QX, 5>(sm, s, stream, sb, dstate); return; }
+
+    DemodState st = dstate[stream];  // local memory: only the scheduler touches it
+    WindowCtl c;
+    c.init(st, sb, so, stream, valid, mode, final_flag);
+    sm.w0[s] = c.w0;
+    sm.live[s] = c.live ? 1 : 0;
+    if (s == 0) sm.exit_flag = 0;
+    __syncthreads();  // (1) symbol 0 published
+    bool any_live = __any_sync(kFull, c.live);
+    while (any_live) {
+        const bool first = c.sym_in_call == 0;
+        bar_sync<kBarZ, 64>();
+        BankLo lo;
+        load_lo(sm, s, lo);
+        wait_window(sm, s, c.live, c.w0);
+        const uint32_t* const win = &sm.ring[c.w0 & (kRingRows - 1)][s];
+        auto slot = [&](int k, double& I, double& Q) { unpack_ring<QX>(win[k * kSpc], k, I, Q); };
+        cplx A[4], B[4], s10, s20, s40;
+        bank_on_blocks(slot, lo.z1, lo.z2, A, B, s10, s20, s40);
+        bar_sync<kBarPow, 64>();
+        BankPow pw;
+        load_pow(sm, s, pw);
+        BankOnTime on;
+        bank_on_time(slot, c.f, lo, pw, A, B, s10, s20, s40, on);
+        const bool tone1 = on.eO1 > on.eO2;  // :272, :291
+        sm.o[0][s] = on.O1.r; sm.o[1][s] = on.O1.i; sm.o[2][s] = on.O2.r; sm.o[3][s] = on.O2.i;
+        sm.flags[s] = (tone1 ? kFlagTone1 : 0) | (first ? kFlagFirst : 0) | (c.live ? kFlagLive : 0);
+        bar_arrive<kBarO, 64>();  // the AFC warp takes it from here
+        if (c.live) c.put_soft(on.eO2 - on.eO1);
+        cplx fixE = {0.0, 0.0};
+        if (first && c.live) fixE = first_fix_cold<QX>(win, c.f, tone1 ? lo.z1 : lo.z2);  // :237, once per call
+        double eE, eL;
+        bank_early_late(slot, c.f, tone1, lo, pw, on, fixE, eE, eL);
+        if (c.live) {
+            bank_timing(eE, eL, c.timing_freq, c.pos, g_fm);
+            c.advance(st, mode, final_flag);
+            if (c.live) st_vol(&sm.w0[s], c.w0);
+            else st_vol(&sm.live[s], 0);
+        }
+        any_live = __any_sync(kFull, c.live);
+    }
+    sm.flags[s] = kFlagExit;
+    st_vol(&sm.exit_flag, 1);
+    bar_arrive<kBarO, 64>();
+    if (valid) c.persist(st, so, dstate, stream, counters);
+    __syncthreads();  // (2)
+}
+
+// =================================================================================================================
+// Four-warp kernel: WINDOW-LO, WINDOW-HI, AFC, STAGE (128 threads).  Roles rotate with the CTA's arrival order on
+// its SM so that the four resident CTAs put one warp of every role on each SM sub-partition.
+__device__ int g_sm_arrivals[1024];
+
+template <int QX>
+__global__ void __launch_bounds__(128, 4)
+demod_bank4_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
+                   int final_flag, double afc_alpha, int rotate, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BankSmem& sm = *reinterpret_cast<BankSmem*>(smem_raw);
+    if (threadIdx.x == 0) {
+        int rot = 0;
+        if (rotate) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            rot = atomicAdd(&g_sm_arrivals[smid & 1023], 1) & 3;
+        }
+        sm.rot = rot;
+        sm.exit_flag = 0;
+    }
+    __syncthreads();  // (0)
+    const int s = threadIdx.x & 31, role = ((threadIdx.x >> 5) + sm.rot) & 3;
+    const int stream_raw = blockIdx.x * kSpc + s;
+    const bool valid = stream_raw < n_streams;
+    const int stream = valid ? stream_raw : n_streams - 1;
+
+    if (role == 2) { role_afc<96>(sm, s, stream, valid, dstate, afc_alpha); return; }
+    if (role == 3) { role_stage<QX, 4>(sm, s, stream, sb, dstate); return; }
+
     if (role == 0) {
-        // ================================================================= WINDOW
+        // ============================================================= WINDOW-LO: H1, H2, on-time, H0, early, timing
         DemodState st = dstate[stream];  // local memory: only the scheduler touches it
-        const long long avail = sb.avail[stream];
-        double* const soft_row = so.soft + (long long)stream * so.stride;
-        const int soft_wrap = so.ring ? (int)so.stride : 0x7fffffff;
-        int soft_idx = (int)soft_pos(so, st.n_sym);  // row position of the next soft symbol
-        int n_new = 0;                               // symbols produced by this launch
-        const long long n_sym0 = st.n_sym, origin0 = st.origin;
-        const long long base_abs = make_row_view(sb, stream, st.origin).base_abs;
-        double timing_freq = st.timing_freq;
-        bool live = valid && schedule_cold(st, mode, avail, final_flag != 0);
-        double pos = st.pos;
-        int sym_in_call = st.sym_in_call;
-        double call_len_d = (double)st.call_len;
-        int origin_rel = (int)(st.origin - base_abs);
-        int w0 = 0;
-        double f = 0.0;
-        if (live) {
-            const int b = __double2int_rz(pos);  // pos >= 0: truncation == floor (:125)
-            f = pos - (double)b;
-            w0 = origin_rel + b - kWinLead;
-        }
-        sm.w0[s] = w0;
-        sm.live[s] = live ? 1 : 0;
-        if (s == 0) sm.exit_flag = 0;
+        WindowCtl c;
+        c.init(st, sb, so, stream, valid, mode, final_flag);
+        sm.w0[s] = c.w0;
+        sm.live[s] = c.live ? 1 : 0;
+        sm.x4w[s] = c.w0; sm.x4f[s] = c.f; sm.x4flags[s] = c.live ? kFlagLive : 0;
         __syncthreads();  // (1) symbol 0 published
-        bool any_live = __any_sync(kFull, live);
+        bool any_live = __any_sync(kFull, c.live);
         while (any_live) {
-            const bool first = sym_in_call == 0;
-            // ---- LO steps of this symbol
-            bar_sync<kBarZ>();
+            const bool first = c.sym_in_call == 0;
+            bar_sync<kBarZ, 96>();
             BankLo lo;
-            lo.z1 = {sm.z[0][s], sm.z[1][s]};
-            lo.z2 = {sm.z[2][s], sm.z[3][s]};
-            lo.inc1 = 0.0; lo.inc2 = 0.0;
-            // ---- the window must be in the ring (normally true: the staging warp runs 2-4 symbols ahead)
-            while (!__all_sync(kFull, !live || ld_vol(&sm.fill[s]) >= w0 + kWin)) {}
-            __threadfence_block();
-            const uint32_t* const win = &sm.ring[w0 & (kRingRows - 1)][s];
+            load_lo(sm, s, lo);
+            wait_window(sm, s, c.live, c.w0);
+            const uint32_t* const win = &sm.ring[c.w0 & (kRingRows - 1)][s];
             auto slot = [&](int k, double& I, double& Q) { unpack_ring<QX>(win[k * kSpc], k, I, Q); };
-            // ---- on-time block sums, both tones
-            cplx A[4], B[4], s10, s20, s40;
-            bank_on_blocks(slot, lo.z1, lo.z2, A, B, s10, s20, s40);
-            // ---- LO powers, gate combination, soft decision
-            bar_sync<kBarPow>();
+            cplx A[2], B[2], s10, s20;
+            bank_two_blocks(slot, 10, lo.z1, lo.z2, A, B, s10, s20);
+            bar_sync<kBarPow, 96>();
             BankPow pw;
-            pw.q1 = {sm.pw[0][s], sm.pw[1][s]};
-            pw.q2 = {sm.pw[2][s], sm.pw[3][s]};
-            pw.qq1 = {sm.pw[4][s], sm.pw[5][s]};
-            pw.qq2 = {sm.pw[6][s], sm.pw[7][s]};
-            pw.zeta40 = {sm.pw[8][s], sm.pw[9][s]};
-            BankOnTime on;
-            bank_on_time(slot, f, lo, pw, A, B, s10, s20, s40, on);
-            const bool tone1 = on.eO1 > on.eO2;  // :272, :291
-            sm.o[0][s] = on.O1.r; sm.o[1][s] = on.O1.i; sm.o[2][s] = on.O2.r; sm.o[3][s] = on.O2.i;
-            sm.flags[s] = (tone1 ? kFlagTone1 : 0) | (first ? kFlagFirst : 0) | (live ? kFlagLive : 0);
-            bar_arrive<kBarO>();  // the AFC warp takes it from here
-            if (live) {
-                soft_row[soft_idx] = on.eO2 - on.eO1;  // :268
-                if (++soft_idx == soft_wrap) soft_idx = 0;
-                ++n_new;
+            load_pow(sm, s, pw);
+            const cplx P1 = cfma(pw.q1, A[1], A[0]), P2 = cfma(pw.q2, B[1], B[0]);
+            // ---- the HI warp's half
+            bar_sync<kBarX1, 64>();
+            const cplx R1 = {sm.x1[0][s], sm.x1[1][s]}, R2 = {sm.x1[2][s], sm.x1[3][s]};
+            const cplx s50 = {sm.x1[10][s], sm.x1[11][s]};
+            cplx O1, O2;
+            double eO1, eO2;
+            bank_on_time_from_halves(c.f, lo, pw, P1, P2, R1, R2, s10, s50, O1, O2, eO1, eO2);
+            const bool tone1 = eO1 > eO2;  // :272, :291
+            sm.o[0][s] = O1.r; sm.o[1][s] = O1.i; sm.o[2][s] = O2.r; sm.o[3][s] = O2.i;
+            sm.flags[s] = (tone1 ? kFlagTone1 : 0) | (first ? kFlagFirst : 0) | (c.live ? kFlagLive : 0);
+            bar_arrive<kBarO, 64>();  // the AFC warp takes it from here
+            {
+                const cplx H2 = tone1 ? A[1] : B[1];
+                sm.x2[0][s] = H2.r; sm.x2[1][s] = H2.i; sm.x2[2][s] = s20.r; sm.x2[3][s] = s20.i;
+                sm.x2flags[s] = tone1 ? kFlagTone1 : 0;
             }
-            // ---- early / late gates of the dominant tone, timing loop
+            bar_arrive<kBarX2, 64>();  // the HI warp can finish the late gate
+            if (c.live) c.put_soft(eO2 - eO1);
+            // ---- early gate of the dominant tone
+            const cplx zd = tone1 ? lo.z1 : lo.z2;
             cplx fixE = {0.0, 0.0};
-            if (first && live) fixE = first_fix_cold(win, f, tone1 ? lo.z1 : lo.z2);  // :237, once per call
-            double eE, eL;
-            bank_early_late(slot, f, tone1, lo, pw, on, fixE, eE, eL);
-            if (live) {
-                bank_timing(eE, eL, timing_freq, pos, g_fm);
-                sym_in_call = 1;  // any non-zero value: the open call has produced symbols
-                // ---- next symbol of this stream
-                if (!((pos + 40.0) + 10.0 < call_len_d)) {  // :221 fails: close the call, maybe open the next
-                    st.n_sym = n_sym0 + n_new;
-                    st.sym_in_call = sym_in_call;
-                    st.pos = pos;
-                    live = schedule_cold(st, mode, avail, final_flag != 0);
-                    pos = st.pos;
-                    sym_in_call = st.sym_in_call;
-                    call_len_d = (double)st.call_len;
-                    origin_rel = (int)(st.origin - base_abs);
-                }
-                if (live) {
-                    const int b2 = __double2int_rz(pos);
-                    w0 = origin_rel + b2 - kWinLead;
-                    f = pos - (double)b2;
-                    st_vol(&sm.w0[s], w0);
-                } else {
-                    st_vol(&sm.live[s], 0);
-                }
+            if (first && c.live) fixE = first_fix_cold<QX>(win, c.f, zd);  // :237, once per call
+            cplx H0, s0;
+            bank_block_one(slot, 0, zd, H0, s0);
+            const cplx H3 = tone1 ? cplx{sm.x1[4][s], sm.x1[5][s]} : cplx{sm.x1[6][s], sm.x1[7][s]};
+            const cplx s40 = {sm.x1[8][s], sm.x1[9][s]};
+            const double eE = bank_gate_energy(c.f, zd, tone1 ? pw.q1 : pw.q2, tone1 ? pw.qq1 : pw.qq2,
+                                               bank_z40(pw.zeta40, tone1 ? 0 : 1), H0, tone1 ? P1 : P2, H3, s40, s0, fixE);
+            bar_sync<kBarX3, 64>();
+            const double eL = sm.x3[s];
+            if (c.live) {
+                bank_timing(eE, eL, c.timing_freq, c.pos, g_fm);
+                c.advance(st, mode, final_flag);
+                if (c.live) st_vol(&sm.w0[s], c.w0);
+                else st_vol(&sm.live[s], 0);
             }
-            any_live = __any_sync(kFull, live);
+            any_live = __any_sync(kFull, c.live);
+            sm.x4w[s] = c.w0; sm.x4f[s] = c.f;
+            sm.x4flags[s] = (c.live ? kFlagLive : 0) | (any_live ? 0 : kFlagExit);
+            bar_arrive<kBarX4, 64>();
         }
-        // ---- tell the other roles to stop
         sm.flags[s] = kFlagExit;
         st_vol(&sm.exit_flag, 1);
-        bar_arrive<kBarO>();
-        // ---- persist the streams' state: this warp writes the record, the AFC warp then patches its fields
-        if (valid) {
-            st.n_sym = n_sym0 + n_new;
-            st.sym_in_call = sym_in_call;
-            st.pos = pos; st.timing_freq = timing_freq;
-            so.n_sym[stream] = st.n_sym;
-            DemodState* d = dstate + stream;
-            d->pos = st.pos; d->timing_freq = st.timing_freq; d->origin = st.origin; d->call_len = st.call_len;
-            d->n_sym = st.n_sym; d->sym_in_call = st.sym_in_call; d->flags = st.flags;
-            unsigned long long dsym = (unsigned long long)(st.n_sym - n_sym0);
-            unsigned long long dsmp = (unsigned long long)(st.origin - origin0);
-            if (st.flags & kFlagDone) dsmp = (unsigned long long)(avail - origin0);
-            if (dsym) atomicAdd(&counters[kCtrSymbols], dsym);
-            if (dsmp) atomicAdd(&counters[kCtrSamples], dsmp);
-        }
-    } else if (role == 1) {
-        // ================================================================= AFC
-        const DemodState* d0 = dstate + stream;
-        BankAfc afc = {d0->freq_offset, d0->ph1, d0->ph2, d0->p1, d0->p2};
-        BankLo lo;
-        BankPow pw;
-        {
-            double d;
-            const cplx zeta = bank_zeta_general(afc.freq_offset, d);  // a -o offset may exceed the fast range
-            bank_lo_from_zeta(zeta, d, lo, g_fm);
-            bank_pow_from_zeta(zeta, pw, g_bk);
-        }
-        __syncthreads();  // (1)
-        auto publish_z = [&]() {
-            sm.z[0][s] = lo.z1.r; sm.z[1][s] = lo.z1.i; sm.z[2][s] = lo.z2.r; sm.z[3][s] = lo.z2.i;
-            bar_arrive<kBarZ>();
-        };
-        auto publish_pow = [&]() {
-            sm.pw[0][s] = pw.q1.r; sm.pw[1][s] = pw.q1.i; sm.pw[2][s] = pw.q2.r; sm.pw[3][s] = pw.q2.i;
-            sm.pw[4][s] = pw.qq1.r; sm.pw[5][s] = pw.qq1.i; sm.pw[6][s] = pw.qq2.r; sm.pw[7][s] = pw.qq2.i;
-            sm.pw[8][s] = pw.zeta40.r; sm.pw[9][s] = pw.zeta40.i;
-            bar_arrive<kBarPow>();
-        };
-        publish_z();
-        publish_pow();
-        for (;;) {
-            bar_sync<kBarO>();
-            const int fl = sm.flags[s];
-            if (fl & kFlagExit) break;  // warp-uniform: the window warp sets it on every lane
-            const cplx O1 = {sm.o[0][s], sm.o[1][s]}, O2 = {sm.o[2][s], sm.o[3][s]};
-            // no AFC update on the first symbol of a call (:289): same LO steps next symbol
-            const bool update = (fl & kFlagLive) && !(fl & kFlagFirst);
-            cplx zeta = {1.0, 0.0};
-            if (fl & kFlagLive) {
-                bank_afc(afc, O1, O2, (fl & kFlagTone1) != 0, pw.zeta40, lo.inc1, lo.inc2, (fl & kFlagFirst) != 0,
-                         afc_alpha, g_fm);
-                if (update) {
-                    double d;
-                    zeta = bank_zeta_fast(afc.freq_offset, d, g_fm);  // |offset| <= 2 kHz after the clamp (:303)
-                    bank_lo_from_zeta(zeta, d, lo, g_fm);
-                }
-            }
-            publish_z();  // z goes out first: the next symbol's Horner needs nothing else
-            if (update) bank_pow_from_zeta(zeta, pw, g_bk);
-            publish_pow();
-        }
-        __syncthreads();  // (2) the window warp has written the records
-        if (valid) {
-            DemodState* d = dstate + stream;
-            d->freq_offset = afc.freq_offset; d->ph1 = afc.ph1; d->ph2 = afc.ph2; d->p1 = afc.p1; d->p2 = afc.p2;
-        }
-        return;
+        bar_arrive<kBarO, 64>();
+        if (valid) c.persist(st, so, dstate, stream, counters);
+        __syncthreads();  // (2)
     } else {
-        // ================================================================= STAGE
-        const RowView view = make_row_view(sb, stream, dstate[stream].origin);  // same base as the window warp
-        const bool wide = ((reinterpret_cast<uintptr_t>(sb.iq) | (uintptr_t)(sb.stride * 4)) & 31u) == 0;
-        sm.fill[s] = -(1 << 30);
+        // ============================================================= WINDOW-HI: H3, H4, H5 (both tones), late gate
         __syncthreads();  // (1)
-        int req;  // samples [.., req) of this lane's row have been requested (multiple of 8)
-        {
-            const int w0 = sm.w0[s];
-            req = (w0 < 0 ? 0 : w0) & ~(kChunk - 1);
-        }
-        uint4 bufA[2 * kBatchChunks], bufB[2 * kBatchChunks];
-        int idxA = -1, idxB = -1;  // row index of the batch held in the buffer (-1: empty)
-        auto request = [&](uint4 (&buf)[2 * kBatchChunks], int& idx) {
-            const int w0 = ld_vol(&sm.w0[s]);
-            const bool can = ld_vol(&sm.live[s]) != 0 && req + kBatch <= w0 + kRingRows - kChunk && req < view.rel_end;
-            idx = -1;
-            if (can) {
-#pragma unroll
-                for (int c = 0; c < kBatchChunks; ++c) chunk_load(view, req + kChunk * c, wide, buf[2 * c], buf[2 * c + 1]);
-                idx = req;
-                req += kBatch;
-            }
-            return can;
-        };
-        auto retire = [&](uint4 (&buf)[2 * kBatchChunks], int& idx) {
-            const bool had = idx >= 0;
-            if (had) {
-#pragma unroll
-                for (int c = 0; c < kBatchChunks; ++c) chunk_store(sm, s, idx + kChunk * c, buf[2 * c], buf[2 * c + 1]);
-                __threadfence_block();
-                st_vol(&sm.fill[s], idx + kBatch);
-                idx = -1;
-            }
-            return had;
-        };
-        for (;;) {
-            bool work = request(bufA, idxA);
-            work |= retire(bufB, idxB);
-            work |= request(bufB, idxB);
-            work |= retire(bufA, idxA);
-            if (!__any_sync(kFull, work)) {
-                if (ld_vol(&sm.exit_flag)) break;
-                __nanosleep(200);
-            }
+        int w0 = sm.x4w[s];
+        double f = sm.x4f[s];
+        int fl = sm.x4flags[s];
+        bool any_live = __any_sync(kFull, (fl & kFlagLive) != 0);
+        while (any_live) {
+            const bool live = (fl & kFlagLive) != 0;
+            bar_sync<kBarZ, 96>();
+            BankLo lo;
+            load_lo(sm, s, lo);
+            wait_window(sm, s, live, w0);
+            const uint32_t* const win = &sm.ring[w0 & (kRingRows - 1)][s];
+            auto slot = [&](int k, double& I, double& Q) { unpack_ring<QX>(win[k * kSpc], k, I, Q); };
+            cplx C[2], D[2], s30, s40, s50;
+            bank_two_blocks(slot, 30, lo.z1, lo.z2, C, D, s30, s40);
+            slot(50, s50.r, s50.i);
+            bar_sync<kBarPow, 96>();
+            BankPow pw;
+            load_pow(sm, s, pw);
+            const cplx R1 = cfma(pw.q1, C[1], C[0]), R2 = cfma(pw.q2, D[1], D[0]);
+            sm.x1[0][s] = R1.r; sm.x1[1][s] = R1.i; sm.x1[2][s] = R2.r; sm.x1[3][s] = R2.i;
+            sm.x1[4][s] = C[0].r; sm.x1[5][s] = C[0].i; sm.x1[6][s] = D[0].r; sm.x1[7][s] = D[0].i;
+            sm.x1[8][s] = s40.r; sm.x1[9][s] = s40.i; sm.x1[10][s] = s50.r; sm.x1[11][s] = s50.i;
+            bar_arrive<kBarX1, 64>();
+            // ---- H5 of both tones while the LO warp decides the dominant tone
+            cplx H5a, H5b, s60;
+            bank_block_both(slot, 50, lo.z1, lo.z2, H5a, H5b);
+            slot(60, s60.r, s60.i);
+            bar_sync<kBarX2, 64>();
+            const bool tone1 = (sm.x2flags[s] & kFlagTone1) != 0;
+            const cplx H2 = {sm.x2[0][s], sm.x2[1][s]}, s20 = {sm.x2[2][s], sm.x2[3][s]};
+            const double eL = bank_gate_energy(f, tone1 ? lo.z1 : lo.z2, tone1 ? pw.q1 : pw.q2, tone1 ? pw.qq1 : pw.qq2,
+                                               bank_z40(pw.zeta40, tone1 ? 0 : 1), H2, tone1 ? R1 : R2, tone1 ? H5a : H5b,
+                                               s60, s20, cplx{0.0, 0.0});
+            sm.x3[s] = eL;
+            bar_arrive<kBarX3, 64>();
+            // ---- next symbol
+            bar_sync<kBarX4, 64>();
+            w0 = sm.x4w[s];
+            f = sm.x4f[s];
+            fl = sm.x4flags[s];
+            any_live = !(fl & kFlagExit);  // warp-uniform: the LO warp sets it on every lane
         }
         __syncthreads();  // (2)
-        return;
     }
-    __syncthreads();  // (2) window warp
 }
 
 template <int QX>
@@ -369,18 +563,42 @@ static cudaError_t launch_bank_t(const StreamBuffers& sb, const SoftBuffers& so,
     cudaError_t e = cudaFuncSetAttribute(demod_bank_kernel<QX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (n_streams + kSpc - 1) / kSpc;
-    demod_bank_kernel<QX><<<grid, kThreads, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
+    demod_bank_kernel<QX><<<grid, 96, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
+    return cudaGetLastError();
+}
+template <int QX>
+static cudaError_t launch_bank4_t(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams, int mode,
+                                  int final_flag, double afc_alpha, int rotate, unsigned long long* counters, cudaStream_t st) {
+    const size_t smem = sizeof(BankSmem);
+    cudaError_t e = cudaFuncSetAttribute(demod_bank4_kernel<QX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (n_streams + kSpc - 1) / kSpc;
+    demod_bank4_kernel<QX><<<grid, 128, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, rotate, counters);
     return cudaGetLastError();
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// OPVD_BANK_QX / OPVD_BANK_ROTATE: development switches (conversion split, role rotation); results are identical
 cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                               cudaStream_t st) {
-    // OPVD_BANK_QX: development switch for the conversion split (see unpack_ring); every value gives identical results
-    static const int qx = [] { const char* e = getenv("OPVD_BANK_QX"); return e ? atoi(e) : 1; }();
+    static const int qx = env_int("OPVD_BANK_QX", 1);
     if (qx == 0) return launch_bank_t<0>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     if (qx == 2) return launch_bank_t<2>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     return launch_bank_t<1>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+}
+
+cudaError_t launch_demod_bank4(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
+                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
+                               cudaStream_t st) {
+    static const int qx = env_int("OPVD_BANK_QX", 2), rotate = env_int("OPVD_BANK_ROTATE", 1);
+    if (qx == 0) return launch_bank4_t<0>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, rotate, counters, st);
+    if (qx == 1) return launch_bank4_t<1>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, rotate, counters, st);
+    return launch_bank4_t<2>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, rotate, counters, st);
 }
 
 }  // namespace opvd

@@ -21,9 +21,12 @@ __constant__ int16_t c_tsin[160];
 __constant__ int16_t c_tcos[160];
 __constant__ uint8_t c_lfsr_tx[kFrameBytes];
 
-static bool g_synth_const = false;
+// __constant__ memory is per device: upload once per device ordinal (a multi-GPU host process calls this on every device)
+static bool g_synth_const[64] = {};
 static void upload_synth_constants() {
-    if (g_synth_const) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && g_synth_const[dev]) return;
     int16_t ts[160], tc[160];
     for (int k = 0; k < 160; ++k) {
         ts[k] = (int16_t)(16383.0 * std::sin(kTwoPi * k / 160.0));
@@ -42,7 +45,7 @@ static void upload_synth_constants() {
     cudaMemcpyToSymbol(c_tsin, ts, sizeof(ts));
     cudaMemcpyToSymbol(c_tcos, tc, sizeof(tc));
     cudaMemcpyToSymbol(c_lfsr_tx, lf, sizeof(lf));
-    g_synth_const = true;
+    if (dev >= 0 && dev < 64) g_synth_const[dev] = true;
 }
 
 __host__ __device__ inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser

@@ -16,6 +16,16 @@ struct FrameTask {
     int64_t payload_start;  // absolute symbol index of the first payload soft symbol
 };
 
+// One decoded frame in the contiguous log the host polls: the decoder appends the frames of every run in task order
+// (in order within a stream), so a poll copies only what is new.  176 bytes.
+struct FrameLogEntry {
+    int32_t stream, frame_idx, metric, reserved;
+    int64_t payload_start, ready_idx;
+    double quality;
+    uint8_t frame[kFrameBytes];
+    uint8_t pad[2];
+};
+
 // device-side counters (uint64 each); reduced across ranks by the caller
 enum Counter : int {
     kCtrSamples = 0,     // samples consumed by the demodulator (call origins advanced + last call)
@@ -96,10 +106,9 @@ __device__ __forceinline__ long long soft_pos(const SoftBuffers& so, long long n
 void launch_estimate(const StreamBuffers& sb, DemodState* dstate, double* est_out, int n_streams, int mode,
                      int final_flag, cudaStream_t st);
 
-// lanes_per_stream in {1, 2, 4, 32, 64}; 0 = chosen from the stream count; returns cudaError
-//   1/2/4  lane kernels (kernels_demod.cu)    32  warp per stream (kernels_demod_warp.cu)
-//   64     batched: 32 streams per 128-thread CTA (kernels_demod_batch.cu)
-//   128    pipelined batched: 2 x 32 streams per 128-thread CTA (kernels_demod_pipe.cu)
+// lanes_per_stream in {32, 96, 128}; 0 = chosen from the stream count (demod_select.cu); returns cudaError
+//   32   warp per stream (kernels_demod_warp.cu)
+//   96   channel bank, three role warps per 32 streams      128  four role warps (kernels_demod_bank.cu)
 cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                          int mode, int final_flag, double afc_alpha, int lanes_per_stream,
                          unsigned long long* counters, cudaStream_t st);
@@ -112,21 +121,16 @@ cudaError_t launch_demod_warp(const StreamBuffers& sb, const SoftBuffers& so, De
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                               cudaStream_t st);
 
-// batched variant (kernels_demod_batch.cu); selected by launch_demod for lanes_per_stream == 64
-cudaError_t launch_demod_batch(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
-                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
-                               cudaStream_t st);
-
 // channel-bank variant (kernels_demod_bank.cu): 32 streams per 96-thread CTA, three free-running role warps;
 // selected by launch_demod for lanes_per_stream == 96
 cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                               cudaStream_t st);
 
-// pipelined batched variant (kernels_demod_pipe.cu); selected by launch_demod for lanes_per_stream == 128
-cudaError_t launch_demod_pipe(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
-                              int mode, int final_flag, double afc_alpha, unsigned long long* counters,
-                              cudaStream_t st);
+// four-warp channel-bank variant (two window warps per 32 streams); lanes_per_stream == 128
+cudaError_t launch_demod_bank4(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
+                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
+                               cudaStream_t st);
 
 // coherent mode (kernels_demod_coherent.cu): `opv-demod -c`, batch only
 cudaError_t launch_demod_coherent(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
@@ -139,8 +143,8 @@ void launch_track(const SoftBuffers& so, TrackState* tstate, int n_streams,
                   cudaStream_t st);
 
 void launch_decode(const SoftBuffers& so, const FrameTask* tasks, const int32_t* n_tasks_dev, int n_tasks_host,
-                   uint8_t* frames, int32_t* metrics, int max_frames, unsigned long long* counters,
-                   cudaStream_t st);
+                   uint8_t* frames, int32_t* metrics, int max_frames, const FrameRec* frec, FrameLogEntry* log,
+                   unsigned long long* log_count, long long log_cap, unsigned long long* counters, cudaStream_t st);
 
 // stage-level entry (FrameDecoder::decode seam): payloads [n][2144] doubles -> frames [n][134], metrics [n]
 void launch_decode_payloads(const double* payloads, int n, uint8_t* frames, int32_t* metrics,

@@ -131,35 +131,43 @@ class DemodBank:
     def demod_variant(self) -> str:
         """Name of the demodulator kernel this bank runs (automatic selection resolved)."""
         lanes = int(self._lib.opvd_demod_lanes(self._h))
-        return {32: "demod_warp_kernel", 64: "demod_batch_kernel", 128: "demod_pipe_kernel"}.get(
-            lanes, f"demod_kernel_t(lanes={lanes})")
+        return {32: "demod_warp_kernel", 96: "demod_bank_kernel", 128: "demod_bank4_kernel"}.get(
+            lanes, f"demod(lanes={lanes})")
 
     # -- output --------------------------------------------------------------------------------
+    _INFO_DTYPE = np.dtype([("stream", np.int32), ("frame_idx", np.int32), ("metric", np.int32), ("reserved", np.int32),
+                            ("payload_start", np.int64), ("ready_idx", np.int64), ("sync_quality", np.float64)])
+
     def poll_frames(self, max_frames: int | None = None) -> Frames:
+        """Frames decoded since the last poll (waits for the enqueued runs): the reference's cout.write stream."""
+        assert self._INFO_DTYPE.itemsize == C.sizeof(capi.FrameInfo)
         chunks, infos = [], []
-        cap = 4096
+        cap = 65536
         remaining = max_frames
         while True:
             want = cap if remaining is None else min(cap, remaining)
             if want <= 0:
                 break
-            buf = np.zeros((want, FRAME_BYTES), np.uint8)
-            info = (capi.FrameInfo * want)()
-            n = self._ck(self._lib.opvd_poll_frames(self._h, want, buf.ctypes.data, info), "opvd_poll_frames")
+            buf = np.empty((want, FRAME_BYTES), np.uint8)
+            info = np.empty(want, self._INFO_DTYPE)
+            n = self._ck(self._lib.opvd_poll_frames(self._h, want, buf.ctypes.data, info.ctypes.data), "opvd_poll_frames")
             if n:
                 chunks.append(buf[:n])
-                infos.extend(info[:n])
+                infos.append(info[:n])
             if remaining is not None:
                 remaining -= n
             if n < want:
                 break
         data = np.concatenate(chunks) if chunks else np.zeros((0, FRAME_BYTES), np.uint8)
-        return Frames(data,
-                      np.array([i.stream for i in infos], np.int32), np.array([i.frame_idx for i in infos], np.int32),
-                      np.array([i.metric for i in infos], np.int32),
-                      np.array([i.payload_start for i in infos], np.int64),
-                      np.array([i.ready_idx for i in infos], np.int64),
-                      np.array([i.sync_quality for i in infos], np.float64))
+        inf = np.concatenate(infos) if infos else np.zeros(0, self._INFO_DTYPE)
+        return Frames(data, inf["stream"].copy(), inf["frame_idx"].copy(), inf["metric"].copy(), inf["payload_start"].copy(),
+                      inf["ready_idx"].copy(), inf["sync_quality"].copy())
+
+    def frames_lost(self) -> int:
+        """Frames overwritten in the device log before they were polled (0 unless polls are too rare)."""
+        v = C.c_uint64()
+        self._ck(self._lib.opvd_frames_lost(self._h, C.byref(v)), "opvd_frames_lost")
+        return int(v.value)
 
     def poll_events(self, stream: int):
         """[(type, sym_idx, count, corr, raw)] — the tracker's stderr lines of the reference."""

@@ -9,8 +9,6 @@
 #include <cmath>
 #include "../../opv_cxx_demod_b200/csrc/demod_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/demod_warp_core.cuh"
-#include "../../opv_cxx_demod_b200/csrc/demod_batch_core.cuh"
-#include "../../opv_cxx_demod_b200/csrc/demod_pipe_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/demod_bank_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/demod_coherent_core.cuh"
 #include "../../opv_cxx_demod_b200/csrc/est_core.cuh"
@@ -165,142 +163,6 @@ size_t hostsim_demod_warp(const int16_t* iq, size_t n, int mode, double afc_alph
     return ns;
 }
 
-// whole stream through the BATCHED decomposition (demod_batch_core.cuh): four helper "threads" per
-// symbol (tone x window half) followed by the serial lane.  Same contract as hostsim_demod.
-static size_t demod_batch_impl(bool split, const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init,
-                               double init_offset, double* soft_out, size_t cap, double* est_out, double* final_freq,
-                               double* final_tfreq) {
-    std::vector<uint32_t> w(n + 64 + 64, 0xDEADBEEFu);
-    for (size_t i = 0; i < n; ++i)
-        w[64 + i] = (uint32_t)(uint16_t)iq[2 * i] | ((uint32_t)(uint16_t)iq[2 * i + 1] << 16);
-    const uint32_t* base = w.data() + 64;
-
-    DemodState st;
-    demod_state_init(st);
-    double est = 0.0;
-    if (mode == kModeBatch) {
-        est = hostsim_estimate(iq, n);
-        st.freq_offset = est;
-    } else if (have_init) {
-        st.freq_offset = init_offset;
-    } else if (n >= (size_t)kChunkSamples) {
-        est = hostsim_estimate(iq, kChunkSamples);
-        st.freq_offset = est;
-    }
-    st.flags |= kFlagEstDone;
-    BatchRegs r;
-    r.freq_offset = st.freq_offset; r.ph1 = st.ph1; r.ph2 = st.ph2; r.pos = st.pos; r.timing_freq = st.timing_freq;
-    r.p1 = st.p1; r.p2 = st.p2;
-    batch_lo(r.freq_offset, r.t1, r.t2);
-    size_t ns = 0;
-    while (demod_schedule(st, r.pos, mode, (int64_t)n, true)) {
-        const int64_t b = (int64_t)r.pos;
-        const double f = r.pos - (double)b;
-        const uint32_t* win = base + st.origin + b - kWinLead;
-        const bool first = st.sym_in_call == 0;
-        HalfGates hg[2][2];
-        for (int tone = 0; tone < 2; ++tone)
-            for (int half = 0; half < 2; ++half) {
-                double I[31], Q[31];
-                for (int j = 0; j < 31; ++j) unpack_iq(win[30 * half + j], I[j], Q[j]);
-                const ToneLo& t = tone ? r.t2 : r.t1;
-                if (!split) {
-                    hg[tone][half] = batch_half_gates(I, Q, t.z, t.q, f, half);
-                } else {  // the pipelined kernel's window worker: block sums by two 5-step chains joined by z^5
-                    const cplx A = horner10_split(I, Q, t.z, t.z5), B = horner10_split(I + 10, Q + 10, t.z, t.z5),
-                               Cc = horner10_split(I + 20, Q + 20, t.z, t.z5);
-                    const cplx s0 = {I[0], Q[0]}, s10 = {I[10], Q[10]}, s20 = {I[20], Q[20]}, s30 = {I[30], Q[30]};
-                    hg[tone][half] = half_gates_from_blocks(A, B, Cc, half ? s10 : s0, half ? s20 : s10, half ? s30 : s20,
-                                                            t.z, t.q, f, half);
-                }
-            }
-        cplx fix1 = {0.0, 0.0}, fix2 = {0.0, 0.0};
-        if (first) { fix1 = first_symbol_fix(win, f, r.t1.z); fix2 = first_symbol_fix(win, f, r.t2.z); }
-        const ToneGates g1 = batch_finish_tone(hg[0][0], hg[0][1], r.t1, fix1);
-        const ToneGates g2 = batch_finish_tone(hg[1][0], hg[1][1], r.t2, fix2);
-        const double soft = batch_symbol_serial(r, g1, g2, first, afc_alpha, g_fm);
-        st.sym_in_call++;
-        if (ns < cap) soft_out[ns] = soft;
-        ++ns;
-        st.n_sym++;
-    }
-    if (est_out) *est_out = est;
-    if (final_freq) *final_freq = r.freq_offset;
-    if (final_tfreq) *final_tfreq = r.timing_freq;
-    return ns;
-}
-
-// whole stream through the BATCHED decomposition (kernels_demod_batch.cu)
-size_t hostsim_demod_batch(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
-                           double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
-    return demod_batch_impl(false, iq, n, mode, afc_alpha, have_init, init_offset, soft_out, cap, est_out, final_freq,
-                            final_tfreq);
-}
-// the same with the pipelined kernel's split block sums (kernels_demod_pipe.cu, lanes_per_stream = 128)
-size_t hostsim_demod_pipe_split(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
-                                double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
-    return demod_batch_impl(true, iq, n, mode, afc_alpha, have_init, init_offset, soft_out, cap, est_out, final_freq,
-                            final_tfreq);
-}
-
-// whole stream through the PIPELINED kernel's decomposition (demod_pipe_core.cuh): four quarter "threads" per
-// symbol (15 window slots each, both tones), one finishing thread per tone, then the serial lane.
-size_t hostsim_demod_pipe(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
-                          double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
-    std::vector<uint32_t> w(n + 64 + 64, 0xDEADBEEFu);
-    for (size_t i = 0; i < n; ++i)
-        w[64 + i] = (uint32_t)(uint16_t)iq[2 * i] | ((uint32_t)(uint16_t)iq[2 * i + 1] << 16);
-    const uint32_t* base = w.data() + 64;
-
-    DemodState st;
-    demod_state_init(st);
-    double est = 0.0;
-    if (mode == kModeBatch) {
-        est = hostsim_estimate(iq, n);
-        st.freq_offset = est;
-    } else if (have_init) {
-        st.freq_offset = init_offset;
-    } else if (n >= (size_t)kChunkSamples) {
-        est = hostsim_estimate(iq, kChunkSamples);
-        st.freq_offset = est;
-    }
-    st.flags |= kFlagEstDone;
-    BatchRegs r;
-    r.freq_offset = st.freq_offset; r.ph1 = st.ph1; r.ph2 = st.ph2; r.pos = st.pos; r.timing_freq = st.timing_freq;
-    r.p1 = st.p1; r.p2 = st.p2;
-    batch_lo(r.freq_offset, r.t1, r.t2);
-    size_t ns = 0;
-    while (demod_schedule(st, r.pos, mode, (int64_t)n, true)) {
-        const int64_t b = (int64_t)r.pos;
-        const double f = r.pos - (double)b;
-        const uint32_t* win = base + st.origin + b - kWinLead;
-        const bool first = st.sym_in_call == 0;
-        QuarterParts qp[2][4];
-        for (int q = 0; q < 4; ++q) {
-            double I[15], Q[15];
-            for (int j = 0; j < 15; ++j) unpack_iq(win[15 * q + j], I[j], Q[j]);
-            qp[0][q] = quarter_parts(I, Q, r.t1.z, r.t1.z5, q);
-            qp[1][q] = quarter_parts(I, Q, r.t2.z, r.t2.z5, q);
-        }
-        cplx edge[6];
-        const int slots[6] = {0, 10, 20, 40, 50, 60};
-        for (int e = 0; e < 6; ++e) unpack_iq(win[slots[e]], edge[e].r, edge[e].i);
-        cplx fix1 = {0.0, 0.0}, fix2 = {0.0, 0.0};
-        if (first) { fix1 = first_symbol_fix(win, f, r.t1.z); fix2 = first_symbol_fix(win, f, r.t2.z); }
-        const ToneGates g1 = finish_tone_quarters(qp[0], edge, r.t1, f, fix1);
-        const ToneGates g2 = finish_tone_quarters(qp[1], edge, r.t2, f, fix2);
-        const double soft = batch_symbol_serial(r, g1, g2, first, afc_alpha, g_fm);
-        st.sym_in_call++;
-        if (ns < cap) soft_out[ns] = soft;
-        ++ns;
-        st.n_sym++;
-    }
-    if (est_out) *est_out = est;
-    if (final_freq) *final_freq = r.freq_offset;
-    if (final_tfreq) *final_tfreq = r.timing_freq;
-    return ns;
-}
-
 // whole stream through the CHANNEL-BANK decomposition (demod_bank_core.cuh, kernels_demod_bank.cu): on-time sums of
 // both tones, early/late sums of the dominant tone only, LO powers from one zeta chain.  Same contract as hostsim_demod.
 size_t hostsim_demod_bank(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
@@ -353,6 +215,89 @@ size_t hostsim_demod_bank(const int16_t* iq, size_t n, int mode, double afc_alph
         bank_timing(eE, eL, timing_freq, pos, g_fm);
         // AFC role
         bank_afc(afc, on.O1, on.O2, tone1, pw.zeta40, lo.inc1, lo.inc2, first, afc_alpha, g_fm);
+        if (!first) {
+            double d;
+            const cplx zeta = bank_zeta_fast(afc.freq_offset, d, g_fm);
+            bank_lo_from_zeta(zeta, d, lo, g_fm);
+            bank_pow_from_zeta(zeta, pw, g_bk);
+        }
+        st.sym_in_call++;
+        if (ns < cap) soft_out[ns] = soft;
+        ++ns;
+        st.n_sym++;
+    }
+    if (est_out) *est_out = est;
+    if (final_freq) *final_freq = afc.freq_offset;
+    if (final_tfreq) *final_tfreq = timing_freq;
+    return ns;
+}
+
+// the same through the FOUR-WARP kernel's decomposition (two window halves, kernels_demod_bank.cu demod_bank4_kernel)
+size_t hostsim_demod_bank4(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
+                           double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
+    std::vector<uint32_t> w(n + 64 + 64, 0xDEADBEEFu);
+    for (size_t i = 0; i < n; ++i)
+        w[64 + i] = (uint32_t)(uint16_t)iq[2 * i] | ((uint32_t)(uint16_t)iq[2 * i + 1] << 16);
+    const uint32_t* base = w.data() + 64;
+
+    DemodState st;
+    demod_state_init(st);
+    double est = 0.0;
+    if (mode == kModeBatch) {
+        est = hostsim_estimate(iq, n);
+        st.freq_offset = est;
+    } else if (have_init) {
+        st.freq_offset = init_offset;
+    } else if (n >= (size_t)kChunkSamples) {
+        est = hostsim_estimate(iq, kChunkSamples);
+        st.freq_offset = est;
+    }
+    st.flags |= kFlagEstDone;
+    BankAfc afc = {st.freq_offset, st.ph1, st.ph2, st.p1, st.p2};
+    BankLo lo;
+    BankPow pw;
+    {
+        double d;
+        const cplx zeta = bank_zeta_general(afc.freq_offset, d);
+        bank_lo_from_zeta(zeta, d, lo, g_fm);
+        bank_pow_from_zeta(zeta, pw, g_bk);
+    }
+    double pos = st.pos, timing_freq = st.timing_freq;
+    size_t ns = 0;
+    while (demod_schedule(st, pos, mode, (int64_t)n, true)) {
+        const int64_t b = (int64_t)pos;
+        const double f = pos - (double)b;
+        const uint32_t* win = base + st.origin + b - kWinLead;
+        const bool first = st.sym_in_call == 0;
+        auto slot = [&](int k, double& I, double& Q) { unpack_iq(win[k], I, Q); };
+        // LO warp: H1, H2; HI warp: H3, H4, s50
+        cplx A[2], B[2], Cc[2], D[2], s10, s20, s30, s40, s50;
+        bank_two_blocks(slot, 10, lo.z1, lo.z2, A, B, s10, s20);
+        bank_two_blocks(slot, 30, lo.z1, lo.z2, Cc, D, s30, s40);
+        slot(50, s50.r, s50.i);
+        const cplx P1 = cfma(pw.q1, A[1], A[0]), P2 = cfma(pw.q2, B[1], B[0]);
+        const cplx R1 = cfma(pw.q1, Cc[1], Cc[0]), R2 = cfma(pw.q2, D[1], D[0]);
+        cplx O1, O2;
+        double eO1, eO2;
+        bank_on_time_from_halves(f, lo, pw, P1, P2, R1, R2, s10, s50, O1, O2, eO1, eO2);
+        const bool tone1 = eO1 > eO2;
+        const double soft = eO2 - eO1;
+        // HI warp: H5 of both tones, late gate
+        cplx H5a, H5b, s60;
+        bank_block_both(slot, 50, lo.z1, lo.z2, H5a, H5b);
+        slot(60, s60.r, s60.i);
+        const cplx zd = tone1 ? lo.z1 : lo.z2, qd = tone1 ? pw.q1 : pw.q2, qqd = tone1 ? pw.qq1 : pw.qq2;
+        const cplx z40 = bank_z40(pw.zeta40, tone1 ? 0 : 1);
+        const double eL = bank_gate_energy(f, zd, qd, qqd, z40, tone1 ? A[1] : B[1], tone1 ? R1 : R2, tone1 ? H5a : H5b, s60,
+                                           s20, cplx{0.0, 0.0});
+        // LO warp: H0 of the dominant tone, early gate, timing
+        cplx fixE = {0.0, 0.0};
+        if (first) fixE = first_symbol_fix(win, f, zd);
+        cplx H0, s0;
+        bank_block_one(slot, 0, zd, H0, s0);
+        const double eE = bank_gate_energy(f, zd, qd, qqd, z40, H0, tone1 ? P1 : P2, tone1 ? Cc[0] : D[0], s40, s0, fixE);
+        bank_timing(eE, eL, timing_freq, pos, g_fm);
+        bank_afc(afc, O1, O2, tone1, pw.zeta40, lo.inc1, lo.inc2, first, afc_alpha, g_fm);
         if (!first) {
             double d;
             const cplx zeta = bank_zeta_fast(afc.freq_offset, d, g_fm);

@@ -55,7 +55,7 @@ def _run_bank(pkg, caps, streaming, **kw):
     return bank
 
 
-@pytest.mark.parametrize("lanes", [1, 2, 4, 32, 64, 96, 128])
+@pytest.mark.parametrize("lanes", [32, 96, 128])
 @pytest.mark.parametrize("streaming", [False, True])
 def test_all_cases_one_bank_vs_oracle_and_golden(streaming, lanes, pkg, cases, ora):
     """All standard captures as ONE ragged multi-stream bank: frames / events / soft / offsets per stream,
@@ -138,8 +138,8 @@ def test_streaming_push_granularity_invariance(pkg, cases, ora):
     bank.close()
 
 
-def test_streaming_unbounded_input_compaction(pkg, ora):
-    """A long stream through a small library-owned buffer (front compaction of samples and soft symbols)."""
+def test_streaming_unbounded_input_ring(pkg, ora):
+    """A long stream through a small library-owned buffer: samples and soft symbols live in rings, nothing is moved."""
     from tools import captures as cap
 
     iq = cap.impair(cap.clean_bert(30), 77, ebn0_db=13.0, cfo_hz=-300.0, lead_gap=1234)
@@ -153,6 +153,43 @@ def test_streaming_unbounded_input_compaction(pkg, ora):
     bank.run(final=True)
     frames.append(bank.poll_frames().data)
     assert np.array_equal(np.concatenate(frames), ref.frames)
+    bank.close()
+
+
+@pytest.mark.parametrize("ppm", [200, -500])
+@pytest.mark.parametrize("lanes", [32, 128])
+def test_clock_offset_long_stream_small_rings(ppm, lanes, pkg, ora):
+    """TX/RX sample-clock offset (the reference's timing loop slips rather than tracks it: its integrator gain is 1e-5),
+    two streams through 3-frame sample rings with runs queued ahead of the polls.  The run bound and the soft ring are
+    sized from the loop's real worst case (39.895 samples per symbol, :283-286), not from samples/40 (round-1 advisor
+    finding), so this holds for any input."""
+    from tools import captures as cap
+
+    ratio = 1.0 + ppm * 1e-6
+    clean = cap.clean_bert(40).astype(np.float64)
+    t = np.arange(int(clean.shape[0] * ratio) - 2) / ratio          # resample: symbol period 40 * ratio samples
+    i0 = t.astype(np.int64)
+    fr = (t - i0)[:, None]
+    res = ((1 - fr) * clean[i0] + fr * clean[i0 + 1])
+    iq = cap.impair(np.rint(res).astype(np.int16), 99, ebn0_db=16.0, lead_gap=777)
+    ref = ora.run(iq, True)
+    bank = pkg.DemodBank(2, streaming=True, max_samples=3 * 86720, max_frames=16, lanes_per_stream=lanes)
+    frames = [[], []]
+    for k, pos in enumerate(range(0, iq.shape[0], 86720)):
+        for s in range(2):
+            bank.push_iq(s, iq[pos:pos + 86720])
+        bank.run(final=False, sync=False)
+        if k % 3 == 2:                                             # several runs in flight between polls
+            f = bank.poll_frames()
+            for s in range(2):
+                frames[s].append(f.of_stream(s))
+    bank.run(final=True)
+    f = bank.poll_frames()
+    assert bank.frames_lost() == 0
+    for s in range(2):
+        frames[s].append(f.of_stream(s))
+        assert np.array_equal(np.concatenate(frames[s]), ref.frames), s
+        assert bank.stream_info(s)["n_symbols"] == ref.soft.size
     bank.close()
 
 
@@ -432,7 +469,7 @@ def test_baseline_config3_long_captures_random_starts_and_dropouts(pkg, ora):
                                frac_delay=float(rng.uniform(0, 1)), lead_gap=int(rng.integers(0, 86720)), dropouts=drops,
                                tail_gap=4000))
     for streaming in (True, False):
-        bank = _run_bank(pkg, caps, streaming, lanes_per_stream=64)
+        bank = _run_bank(pkg, caps, streaming, lanes_per_stream=128)
         fr = bank.poll_frames()
         lost = 0
         for s, c in enumerate(caps):
@@ -486,7 +523,7 @@ def test_abi_error_behaviour(pkg):
     assert L.opvd_strerror(-3).decode() and L.opvd_strerror(-5).decode()
 
 
-@pytest.mark.parametrize("lanes", [32, 64, 96, 128])
+@pytest.mark.parametrize("lanes", [32, 96, 128])
 def test_attached_rows_16_byte_aligned_only(lanes, pkg, ora):
     """opvd_attach_device_iq promises 16-byte row alignment only (stride % 4 == 0): rows whose stride is 4 (mod 8)
     samples are not 32-byte aligned, so the 256-bit staging loads must fall back to 128-bit ones."""

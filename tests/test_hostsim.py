@@ -29,14 +29,10 @@ def sim():
                                 C.c_size_t] + [C.POINTER(C.c_double)] * 3
     H.hostsim_demod_warp.restype = C.c_size_t
     H.hostsim_demod_warp.argtypes = H.hostsim_demod.argtypes
-    H.hostsim_demod_batch.restype = C.c_size_t
-    H.hostsim_demod_batch.argtypes = H.hostsim_demod.argtypes
     H.hostsim_demod_bank.restype = C.c_size_t
     H.hostsim_demod_bank.argtypes = H.hostsim_demod.argtypes
-    H.hostsim_demod_pipe_split.restype = C.c_size_t
-    H.hostsim_demod_pipe_split.argtypes = H.hostsim_demod.argtypes
-    H.hostsim_demod_pipe.restype = C.c_size_t
-    H.hostsim_demod_pipe.argtypes = H.hostsim_demod.argtypes
+    H.hostsim_demod_bank4.restype = C.c_size_t
+    H.hostsim_demod_bank4.argtypes = H.hostsim_demod.argtypes
     H.hostsim_demod_coherent.restype = C.c_size_t
     H.hostsim_demod_coherent.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_void_p, C.c_size_t,
                                          C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -52,7 +48,7 @@ NAMES = ["clean5", "clean12_call", "awgn14", "awgn8", "awgn4", "cfo_p1200_delay"
 
 @pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("variant", ["lane", "warp", "batch", "bank", "pipe_split", "pipe"])
+@pytest.mark.parametrize("variant", ["lane", "warp", "bank", "bank4"])
 def test_device_arithmetic_vs_oracle(name, mode, variant, cases, ora, sim):
     iq = cases[name]
     a = np.ascontiguousarray(iq, np.int16).reshape(-1)
@@ -60,8 +56,8 @@ def test_device_arithmetic_vs_oracle(name, mode, variant, cases, ora, sim):
     ref = ora.run(iq, bool(mode))
     soft = np.zeros(n // 40 + 16)
     est, ff, tf = C.c_double(), C.c_double(), C.c_double()
-    fn = {"lane": sim.hostsim_demod, "warp": sim.hostsim_demod_warp, "batch": sim.hostsim_demod_batch, "bank": sim.hostsim_demod_bank,
-          "pipe_split": sim.hostsim_demod_pipe_split, "pipe": sim.hostsim_demod_pipe}[variant]
+    fn = {"lane": sim.hostsim_demod, "warp": sim.hostsim_demod_warp, "bank": sim.hostsim_demod_bank,
+          "bank4": sim.hostsim_demod_bank4}[variant]
     ns = fn(a.ctypes.data, n, mode, 0.001, 0, 0.0, soft.ctypes.data, soft.size, C.byref(est),
                            C.byref(ff), C.byref(tf))
     soft = soft[:ns]
