@@ -6,17 +6,19 @@ the HBM roofline of the front-end kernel, with the reference's CPU opv-demod tim
 
 Workload at N=1 = BASELINE.json configs[1]: 1,024 streams x 10 s (250 frames, 21.68 M samples,
 86.7 MB each; 88.8 GB resident) of synthetic opv-mod-like captures with AWGN, Eb/N0 swept
-2..10 dB across streams.  N>1: every rank owns its own 1,024 streams ("scaling": "weak").  The
-north-star target configuration (over 16,384 concurrent streams, BASELINE configs[4]) is measured in
-the same run as the `channel_bank` object: 18,944 streams per GPU (4 CTAs x 32 streams on each of the
-148 SMs) x 14 frames, resident in HBM, same chain, same timing rules.  A step = one pass of the
-whole chain (estimate -> demod -> sync tracker -> Viterbi) over the rank's bank in streaming mode
-(`opv-demod -s` semantics), from fresh per-stream state.
+2..10 dB across streams.  N>1: every rank owns its own 1,024 streams ("scaling": "weak").
+A step = one pass of the whole chain (estimate -> demod -> sync tracker -> Viterbi) over the rank's bank
+in streaming mode (`opv-demod -s` semantics), from fresh per-stream state, fed in time tiles (the
+tracker + Viterbi of tile t run on a second CUDA stream while tile t+1 is demodulated).
 
-  value   device-timed (CUDA events on the library's stream), inputs resident in HBM
+  value   device-timed (CUDA events on the library's streams), inputs resident in HBM
   e2e     same chain through the C ABI from pinned HOST buffers: H2D of the samples, run, D2H of
-          the decoded frames, on a bounded duration of the same streams (rate metric)
-  --impl reference   the reference's own CPU opv-demod (oracle/_ref), one process per host core
+          the decoded frames, on a bounded duration of the same streams (rate metric, PCIe-bound)
+  channel_bank           north-star regime (BASELINE configs[4]): 18,944 streams per GPU resident, weak scaling
+  channel_bank_strong    configs[4] as written: ONE 16,384-stream bank split over the N ranks (strong scaling)
+  channel_bank.sustained a bank larger than HBM through push/run/poll from pinned host memory (sample/soft rings)
+  --impl reference       the reference's own CPU opv-demod (oracle/_ref), one process per host core, on full
+                         10-s captures of the same workload
 """
 from __future__ import annotations
 
@@ -35,6 +37,7 @@ FS = 2168000.0
 FRAME_SAMPLES = 86720
 METRIC = "aggregate_demod_msps"
 UNIT = "Msamples/s"
+MAX_LEAD = 4000
 
 
 def parse_args():
@@ -45,13 +48,18 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=1024, help="streams per GPU")
     ap.add_argument("--seconds", type=float, default=10.0, help="capture length per stream")
-    ap.add_argument("--lanes", type=int, default=0, help="GPU lanes per stream (0 = automatic)")
+    ap.add_argument("--lanes", type=int, default=0, help="demodulator kernel variant (0 = automatic)")
+    ap.add_argument("--tiles", type=int, default=10, help="time tiles per step of the headline leg")
     ap.add_argument("--e2e-seconds", type=float, default=0.52, help="capture length per stream for the e2e leg")
     ap.add_argument("--e2e-tiles", type=int, default=8, help="time tiles per e2e step (H2D of a tile overlaps the kernels of the previous one)")
     ap.add_argument("--bank-streams", type=int, default=0,
                     help="streams per GPU of the channel-bank leg (0 = 4 CTAs x 32 streams per SM, 18,944 on a B200)")
-    ap.add_argument("--bank-frames", type=int, default=14, help="frames per stream of the channel-bank leg")
-    ap.add_argument("--no-bank", action="store_true", help="skip the >=16,384-stream channel-bank leg")
+    ap.add_argument("--bank-frames", type=int, default=14, help="frames per stream of the channel-bank legs")
+    ap.add_argument("--bank-tiles", type=int, default=7, help="time tiles per step of the channel-bank legs")
+    ap.add_argument("--strong-streams", type=int, default=16384, help="total streams of the strong-scaling bank")
+    ap.add_argument("--sustained-tiles", type=int, default=30, help="one-frame tiles pushed from pinned host memory in the sustained leg")
+    ap.add_argument("--no-bank", action="store_true", help="skip the channel-bank legs")
+    ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -130,7 +138,7 @@ def load_profile_json(name):
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_run(captures, threads):
     """Time the reference's CPU opv-demod (-s -r -q), one process per capture, all started together.
-    captures: list of int16 [n,2] arrays.  Returns (wall_s, total_samples, total_frames, outputs)."""
+    captures: list of int16 [n,2] arrays.  Returns (wall_s, total_samples, total_frames, outputs, kind, threads)."""
     from oracle import oracle as ora
 
     binary = ora.REF_DEMOD if os.path.exists(ora.REF_DEMOD) else None
@@ -149,9 +157,7 @@ def cpu_reference_run(captures, threads):
             outs = [p.communicate()[0] for p in procs]
             wall = time.perf_counter() - t0
             kind = "reference"
-        else:  # the oracle port (single C restatement per capture, threads via processes is not available)
-            import numpy as np
-
+        else:  # the oracle port (single C restatement per capture)
             t0 = time.perf_counter()
             outs = [ora.run(c, True, want_soft=False).frames.tobytes() for c in captures]
             wall = time.perf_counter() - t0
@@ -167,19 +173,40 @@ def cpu_reference_run(captures, threads):
     return wall, samples, frames, outs, kind, threads
 
 
-def reference_arm(args):
-    """--impl reference: the reference's own CPU implementation on all host cores, same metric/config."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
+def cpu_captures(n_caps, n_frames):
+    """Full-length captures of the headline workload for the CPU arm: clean opv-mod BERT capture (TX restatement,
+    bit-identical to the reference's opv-mod) + per-capture AWGN swept 2..10 dB, scaled 0.25, random lead."""
     import numpy as np
 
     from tools import captures as cap
 
+    base = cap.clean_bert(n_frames).astype(np.float32) * np.float32(0.25)
+    a = cap.AMP * 0.25
+    out = []
+    for k in range(n_caps):
+        rng = np.random.default_rng(1000 + k)
+        ebn0 = 2.0 + 8.0 * (k % 64) / 63.0
+        sd = np.float32(np.sqrt(a * a * cap.SPS / (0.5 * 10.0 ** (ebn0 / 10.0)) / 2.0))
+        lead = (k * 997) % MAX_LEAD
+        x = rng.standard_normal((base.shape[0] + lead, 2), dtype=np.float32)
+        x *= sd
+        x[lead:] += base
+        np.rint(x, out=x)
+        np.clip(x, -32768, 32767, out=x)
+        out.append(x.astype(np.int16))
+    return out
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation on all host cores, same metric/config: every process
+    demodulates a FULL capture of the headline workload (args.seconds per stream), so the fixed cost of
+    estimate_offset (src/opv-demod.cpp:1030-1038) weighs what it weighs in the real workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
     cores = os.cpu_count() or 1
-    frames_per_proc = 40  # ~3.5 M samples, ~0.5 s of CPU per process and step
-    base = cap.clean_bert(frames_per_proc)
-    caps = [cap.impair(base, 1000 + k, ebn0_db=2.0 + 8.0 * (k % 64) / 63.0, lead_gap=(k * 997) % 4000) for k in range(cores)]
+    n_frames = int(round(args.seconds * FS / FRAME_SAMPLES))
+    caps = cpu_captures(cores, n_frames)
     times, samples, frames = [], 0, 0
     kind = "reference"
     for it in range(args.warmup + args.steps):
@@ -190,15 +217,15 @@ def reference_arm(args):
             frames += f
     total = sum(times)
     value = samples / total / 1e6
+    sample = (f"{cores} of the {args.streams} streams per step, each a full {args.seconds:g} s capture ({n_frames} frames), "
+              f"one opv-demod -s -r -q process per core")
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / max(len(times), 1), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.streams, args.seconds),
-                   "sample": f"{cores} streams x {frames_per_proc} frames per step, one opv-demod -s -r -q process per core"},
+        "config": {"workload": workload_name(args.streams, args.seconds), "sample": sample},
         "frames_per_s": round(frames / total, 2),
-        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{cores} x {frames_per_proc}-frame captures per step"},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -207,31 +234,40 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_channel_bank(args, pkg, torch, dev, local_rank, rank, world, barrier, reduce_max_ms, reduce_counters, peak, mb):
-    """BASELINE configs[4] / north-star target: a bank of over 16,384 concurrent streams per GPU, resident in
-    HBM (distinct memory per stream), demodulated from fresh state.  Per-GPU work is fixed (weak scaling)."""
-    sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    S = args.bank_streams or 4 * 32 * sms          # 4 resident CTAs x 32 streams on every SM: 18,944 on a B200
-    n_frames = args.bank_frames
-    max_lead = 4000
-    n = n_frames * FRAME_SAMPLES + max_lead + 4000
+def tile_ends(n, n_frames, tiles):
+    """Sample counts at which the resident captures become visible: `tiles` time tiles of whole frames."""
+    tiles = max(1, min(tiles, n_frames))
+    return [MAX_LEAD + FRAME_SAMPLES * (n_frames * (t + 1) // tiles) for t in range(tiles - 1)] + [n]
+
+
+def tiled_step(bank, ptr, stride, ends, keepalive):
+    """One pass over a resident bank from fresh state, fed in time tiles; returns the accumulated device times."""
+    bank.reset()
+    for k, e in enumerate(ends):
+        bank.attach_device_iq(ptr, stride, e, keepalive=keepalive)
+        bank.run(final=(k == len(ends) - 1), sync=False)
+    bank.sync()
+    return bank.last_run_ms()
+
+
+def run_bank_leg(args, pkg, torch, dev, local_rank, world, S, first_stream, n_frames, tiles, seed, barrier, reduce_max_ms,
+                 reduce_counters, peak, mb, label):
+    """A resident bank of S streams per rank (distinct memory per stream), demodulated from fresh state."""
+    n = n_frames * FRAME_SAMPLES + MAX_LEAD + 4000
     stride = (n + 63) // 64 * 64
     buf = torch.empty((S, stride), dtype=torch.int32, device=dev)
-    sp = pkg.make_synth(S, n_frames, stride, n, seed=20261018, ebn0_lo_db=2.0, ebn0_hi_db=10.0, max_lead=max_lead,
-                        first_stream=rank * S)
+    sp = pkg.make_synth(S, n_frames, stride, n, seed=seed, ebn0_lo_db=2.0, ebn0_hi_db=10.0, max_lead=MAX_LEAD,
+                        first_stream=first_stream)
     pkg.synth_bank(buf.data_ptr(), sp, device=local_rank)
     bank = pkg.DemodBank(S, streaming=True, device=local_rank, lanes_per_stream=args.lanes)
-    bank.attach_device_iq(buf.data_ptr(), stride, n, keepalive=buf)
+    ends = tile_ends(n, n_frames, tiles)
     steps, warm = max(2, min(args.steps, 3)), 3
     per = {"estimate": 0.0, "demod": 0.0, "track": 0.0, "decode": 0.0, "total": 0.0}
     for _ in range(warm):
-        bank.reset()
-        bank.run(final=True, sync=True)
+        tiled_step(bank, buf.data_ptr(), stride, ends, buf)
     barrier()
     for _ in range(steps):
-        bank.reset()
-        bank.run(final=True, sync=True)
-        ms = bank.last_run_ms()
+        ms = tiled_step(bank, buf.data_ptr(), stride, ends, buf)
         for k in per:
             per[k] += ms[k]
     barrier()
@@ -246,31 +282,92 @@ def run_channel_bank(args, pkg, torch, dev, local_rank, rank, world, barrier, re
     demod_ms = per["demod"] / steps
     ach = c["samples"] * 4 / (demod_ms * 1e-3) / 1e9
     out = {
-        "workload": f"{S} streams x {n_frames} frames per GPU ({S * n * 4 / 1e9:.1f} GB resident, distinct memory per "
-                    f"stream), AWGN Eb/N0 2-10 dB, stream mode, fresh state every step",
-        "streams_per_gpu": S, "streams_total": S * world, "frames_per_stream": n_frames, "steps": steps, "warmup": warm,
+        "workload": f"{label}: {S} streams x {n_frames} frames per GPU ({S * n * 4 / 1e9:.1f} GB resident, distinct memory "
+                    f"per stream), AWGN Eb/N0 2-10 dB, stream mode, fresh state every step, {len(ends)} time tiles per step",
+        "streams_per_gpu": S, "streams_total": tot_streams(S, world, dev, reduce_counters), "frames_per_stream": n_frames,
+        "steps": steps, "warmup": warm, "tiles_per_step": len(ends),
         "value": round(value, 2), "unit": UNIT, "frames_per_s": round(tot["frames_decoded"] * steps / (dev_ms * 1e-3), 1),
         "ms_per_step": round(dev_ms / steps, 3),
         "kernel_ms_per_step": {k: round(v / steps, 3) for k, v in per.items()},
         "demod_only_msps": round(tot["samples"] * steps / (demod_ms_max * 1e-3) / 1e6, 2),
         "ber": (tot["bit_errors"] / (tot["frames_compared"] * 1072.0)) if tot["frames_compared"] else None,
         "roofline": {"bound": "hbm", "kernel": bank.demod_variant(), "achieved": round(ach, 2), "peak": peak,
-                     "unit": "GB/s", "frac": round(ach / peak, 5), "launch_ms": round(demod_ms, 3),
-                     "algorithmic_bytes_per_launch": int(c["samples"] * 4),
+                     "unit": "GB/s", "frac": round(ach / peak, 5), "launch_ms": round(demod_ms / len(ends), 3),
+                     "launches_per_step": len(ends), "algorithmic_bytes_per_step": int(c["samples"] * 4),
                      "traffic": _traffic(load_profile_json("roofline_traffic.json"), bank.demod_variant(), c["samples"] * 4)},
-        "note": "the estimate kernel is a fixed cost per stream (first 40,000 samples); with 14-frame captures it is a "
-                "visible share of the step, with 10-s captures it is 0.4 %",
+        "note": "total is the elapsed device time of the step: tracker + Viterbi of tile t overlap the demodulator of "
+                "tile t+1, the estimate (first 40,000 samples of every stream) runs once in the first tile",
     }
     if mb:
         dfma = c["samples"] * 12.0 / (demod_ms * 1e-3)
         out["roofline"]["fp64"] = {"achieved_dfma_per_s": round(dfma, 1), "peak_dfma_per_s": mb["dfma_per_s"],
                                    "frac": round(dfma / mb["dfma_per_s"], 4),
-                                   "note": "12 DFMA per sample is the Horner correlator's algorithmic minimum "
-                                           "(60-sample window x 2 tones x 4 per 40 new samples); conversions, gate "
-                                           "combination and the loop arithmetic come on top"}
-    bank.close()
-    del buf
-    torch.cuda.empty_cache()
+                                   "note": "12 DFMA per sample is the Horner correlator's algorithmic count for six full "
+                                           "gates; the kernel evaluates early/late gates for the dominant tone only"}
+    return out, bank, buf, sp
+
+
+def tot_streams(S, world, dev, reduce_counters):
+    return reduce_counters({"s": S}, dev)["s"] if world > 1 else S
+
+
+def run_sustained(args, pkg, torch, np, dev, local_rank, S, bank_buf, barrier, reduce_max_ms):
+    """A bank larger than HBM end to end: S streams fed from pinned host memory in one-frame time tiles through
+    push / run / poll with persistent state (sample and soft-symbol rings, no copies on the device).  The host tile
+    (frame 1 of every stream, frame-aligned) is pushed over and over, so every stream is a continuous periodic
+    capture; a sample of streams is checked bit for bit against the reference binary on the same bytes."""
+    T = args.sustained_tiles
+    host = torch.empty((S, FRAME_SAMPLES), dtype=torch.int32, pin_memory=True)
+    host.copy_(bank_buf[:, MAX_LEAD + FRAME_SAMPLES: MAX_LEAD + 2 * FRAME_SAMPLES])
+    torch.cuda.synchronize()
+    sbank = pkg.DemodBank(S, streaming=True, device=local_rank, max_samples=3 * FRAME_SAMPLES, max_frames=8,
+                          lanes_per_stream=args.lanes)
+    frames = []
+    d2h = 0
+
+    def one_pass():
+        nonlocal d2h
+        sbank.reset()
+        got = []
+        for t in range(T):
+            sbank.push_iq_host_ptr(host.data_ptr(), FRAME_SAMPLES, FRAME_SAMPLES)
+            sbank.run(final=(t == T - 1), sync=False)
+            if t % 4 == 3 or t == T - 1:
+                fr = sbank.poll_frames()
+                d2h += int(fr.data.nbytes + fr.metric.nbytes + fr.payload_start.nbytes)
+                got.append(fr)
+        return got
+
+    one_pass()  # warm-up
+    d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    frames = one_pass()
+    barrier()
+    el = reduce_max_ms(time.perf_counter() - t0, dev)
+    lost = sbank.frames_lost()
+    n_frames = sum(f.data.shape[0] for f in frames)
+    out = {"workload": f"{S} streams x {T} one-frame tiles per GPU from pinned host memory ({S * FRAME_SAMPLES * 4 * T / 1e9:.0f} GB "
+                       f"through a {S * 3 * FRAME_SAMPLES * 4 / 1e9:.1f} GB device ring), poll every 4 tiles",
+           "value": round(S * FRAME_SAMPLES * T / el / 1e6, 2), "unit": UNIT, "seconds": round(el, 3),
+           "h2d_bytes": int(S * FRAME_SAMPLES * 4 * T), "d2h_bytes": d2h, "frames": n_frames, "frames_lost": lost,
+           "h2d_gbs": round(S * FRAME_SAMPLES * 4 * T / el / 1e9, 2)}
+    # parity on a sample of streams against the reference binary on the same (periodic) bytes
+    if int(os.environ.get("RANK", "0")) == 0:
+        from oracle import oracle as ora
+
+        k = min(8, os.cpu_count() or 1)
+        pick = [int(i) for i in np.linspace(0, S - 1, k)]
+        caps = [np.tile(host[s].numpy().view(np.int16).reshape(-1, 2), (T, 1)) for s in pick]
+        _, _, _, outs, kind, _ = cpu_reference_run(caps, k)
+        mism = 0
+        for s, o in zip(pick, outs):
+            ref = np.frombuffer(o, np.uint8).reshape(-1, 134)
+            got = np.concatenate([f.of_stream(s) for f in frames]) if frames else np.zeros((0, 134), np.uint8)
+            mism += 0 if (got.shape == ref.shape and np.array_equal(got, ref)) else 1
+        out["parity"] = {"streams_checked": k, "streams_mismatching": mism, "against": kind}
+    sbank.close()
+    del host
     return out
 
 
@@ -300,17 +397,16 @@ def main():
     S = args.streams                      # per rank (weak scaling)
     lo, hi = stream_range(rank, world, S * world)
     n_frames = int(round(args.seconds * FS / FRAME_SAMPLES))
-    max_lead = 4000
-    n = n_frames * FRAME_SAMPLES + max_lead + 4000
+    n = n_frames * FRAME_SAMPLES + MAX_LEAD + 4000
     stride = (n + 63) // 64 * 64
 
     # ---- synthetic bank, resident in HBM (outside every timed region)
     bank_buf = torch.empty((S, stride), dtype=torch.int32, device=dev)
-    sp = pkg.make_synth(S, n_frames, stride, n, seed=20261017, ebn0_lo_db=2.0, ebn0_hi_db=10.0, max_lead=max_lead,
+    sp = pkg.make_synth(S, n_frames, stride, n, seed=20261017, ebn0_lo_db=2.0, ebn0_hi_db=10.0, max_lead=MAX_LEAD,
                         first_stream=lo)
     pkg.synth_bank(bank_buf.data_ptr(), sp, device=local_rank)
     bank = pkg.DemodBank(S, streaming=True, device=local_rank, lanes_per_stream=args.lanes)
-    bank.attach_device_iq(bank_buf.data_ptr(), stride, n, keepalive=bank_buf)
+    ends = tile_ends(n, n_frames, args.tiles)
 
     def barrier():
         if world > 1:
@@ -318,9 +414,7 @@ def main():
         torch.cuda.synchronize()
 
     def one_step():
-        bank.reset()
-        bank.run(final=True, sync=True)
-        return bank.last_run_ms()
+        return tiled_step(bank, bank_buf.data_ptr(), stride, ends, bank_buf)
 
     for _ in range(args.warmup):
         one_step()
@@ -356,8 +450,9 @@ def main():
     variant = bank.demod_variant()
     roofline = {"bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
                 "traffic": _traffic(traffic, variant, counters["samples"] * 4),
-                "kernel": variant, "launch_ms": round(demod_ms, 3), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(counters["samples"] * 4),
+                "traffic_source": "ncu dram__bytes ratio of a captured launch (profiles/roofline_traffic.json) x this step's bytes",
+                "kernel": variant, "launch_ms": round(demod_ms / len(ends), 3), "launches_per_step": len(ends),
+                "peak_source": peak_src, "algorithmic_bytes_per_step": int(counters["samples"] * 4),
                 "note": "1,024 streams are bound by the per-symbol latency of the serial timing/AFC recurrence "
                         "(one warp per stream, 6.9 warps per SM), not by HBM or a pipe; the HBM/FP64-bound regime "
                         "is the channel_bank object (DESIGN.md section 3)"}
@@ -366,9 +461,15 @@ def main():
         roofline["fp64"] = {"achieved_dfma_per_s": round(counters["samples"] * fp64_ops_per_sample / (demod_ms * 1e-3), 1),
                             "peak_dfma_per_s": mb["dfma_per_s"],
                             "frac": round(counters["samples"] * fp64_ops_per_sample / (demod_ms * 1e-3) / mb["dfma_per_s"], 4)}
-    viterbi = {"acs_per_s": round(counters["acs"] / max(per_kernel["decode"] / args.steps * 1e-3, 1e-9), 1),
-               "decode_ms": round(per_kernel["decode"] / args.steps, 3)}
+    dec_s = max(per_kernel["decode"] / args.steps * 1e-3, 1e-9)
+    viterbi = {"acs_per_s": round(counters["acs"] / dec_s, 1), "decode_ms": round(per_kernel["decode"] / args.steps, 3)}
     if mb:
+        # 15 warp-instructions per trellis step of 64 states (2 per lane) = 7.5 integer lane-operations per ACS
+        viterbi["int_ops_per_acs"] = 7.5
+        viterbi["int32_peak_ops_per_s"] = mb["alu_ops_per_s"]
+        viterbi["frac_of_int32_peak"] = round(viterbi["acs_per_s"] * 7.5 / mb["alu_ops_per_s"], 4)
+        viterbi["fp32_peak_ffma_per_s"] = mb["ffma_per_s"]
+        viterbi["acs_per_ffma_slot"] = round(viterbi["acs_per_s"] / mb["ffma_per_s"], 4)
         viterbi["dpx_peak_ops_per_s"] = mb["dpx_vibmin_add_per_s"]
         viterbi["frac_of_dpx_peak"] = round(viterbi["acs_per_s"] / 2.0 / mb["dpx_vibmin_add_per_s"], 4)  # 2 states per DPX op
 
@@ -376,25 +477,24 @@ def main():
     e2e = None
     if not args.no_e2e:
         nf_e = max(2, int(round(args.e2e_seconds * FS / FRAME_SAMPLES)))
-        n_e = nf_e * FRAME_SAMPLES + max_lead
+        n_e = nf_e * FRAME_SAMPLES + MAX_LEAD
         host = torch.empty((S, n_e), dtype=torch.int32, pin_memory=True)
         host.copy_(bank_buf[:, :n_e])
         torch.cuda.synchronize()
-        ebank = pkg.DemodBank(S, streaming=True, device=local_rank, max_samples=n_e, lanes_per_stream=args.lanes)
-        d2h = 0
-
-        # the capture crosses PCIe in time tiles: the library copies on its own stream, so tile t+1 is in flight
-        # while the kernels of tile t run (stream mode is invariant to how the input is cut, tests/test_gpu_parity.py)
         tiles = max(1, min(args.e2e_tiles, nf_e))
         cuts = [n_e * t // tiles // 64 * 64 for t in range(tiles)] + [n_e]
+        tile_max = max(cuts[t + 1] - cuts[t] for t in range(tiles))
+        # device ring of two tiles + one chunk of carry: tile t+1 crosses PCIe while the kernels of tile t run
+        ebank = pkg.DemodBank(S, streaming=True, device=local_rank, max_samples=2 * tile_max + FRAME_SAMPLES + 256,
+                              lanes_per_stream=args.lanes)
+        d2h = 0
 
         def e2e_step():
             ebank.reset()
             for t in range(tiles):
                 ebank.push_iq_host_ptr(host.data_ptr() + 4 * cuts[t], cuts[t + 1] - cuts[t], n_e)
                 ebank.run(final=(t == tiles - 1), sync=False)
-            fr = ebank.poll_frames()
-            return fr
+            return ebank.poll_frames()
 
         for _ in range(max(1, min(args.warmup, 2))):
             e2e_step()
@@ -409,51 +509,81 @@ def main():
         e_val = S * world * n_e * args.steps / e_s / 1e6
         e2e = {"value": round(e_val, 2), "unit": UNIT, "h2d_bytes_per_step": int(S * n_e * 4), "d2h_bytes_per_step": d2h,
                "sample": f"{S} streams x {nf_e} frames ({n_e} samples) per rank per step from pinned host memory, "
-                         f"pushed and run in {tiles} time tiles",
+                         f"pushed and run in {tiles} time tiles through a {2 * tile_max + FRAME_SAMPLES + 256}-sample device ring "
+                         f"per stream; the rate is bound by the host-to-device copies ({S * n_e * 4 * args.steps / e_s / 1e9:.1f} GB/s "
+                         f"per GPU), so it does not depend on the capture length",
                "frames_per_step": int(fr.data.shape[0])}
         ebank.close()
         del host
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): the reference binary, one process per core
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference binary, one process per core, FULL streams
     cpu_baseline, spot = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        fpp = 60
-        n_c = fpp * FRAME_SAMPLES
-        hostc = bank_buf[:cores, :n_c].cpu().numpy().view(np.int16).reshape(cores, n_c, 2)
+        cores = min(os.cpu_count() or 1, S)
+        hostc = bank_buf[:cores, :n].cpu().numpy().view(np.int16).reshape(cores, n, 2)
         caps = [np.ascontiguousarray(hostc[k]) for k in range(cores)]
         wall, s_c, f_c, outs, kind, thr = cpu_reference_run(caps, cores)
         cpu_baseline = {"value": round(s_c / wall / 1e6, 3), "unit": UNIT, "cores": thr, "kind": kind,
                         "frames_per_s": round(f_c / wall, 2),
-                        "sample": f"first {fpp} frames of streams 0..{cores - 1} of the same bank, one opv-demod -s -r -q per core"}
-        # parity spot check on the same bytes: the reference's frames are a prefix of the GPU's (causal chain)
+                        "sample": f"streams 0..{cores - 1} of the same bank in full ({n_frames} frames, {n} samples each), "
+                                  f"one opv-demod -s -r -q per core"}
+        # parity spot check on the same bytes: every frame of every checked stream, whole-stream compare
         fr = bank.poll_frames()
-        mism, compared = 0, 0
+        mism, compared, bad_streams = 0, 0, 0
         for k, o in enumerate(outs):
             ref = np.frombuffer(o, np.uint8).reshape(-1, 134)
             got = fr.of_stream(k)
-            m = max(ref.shape[0] - 1, 0)
-            compared += m
-            mism += int((ref[:m] != got[:m]).any(axis=1).sum()) if got.shape[0] >= m else m
-        spot = {"streams": cores, "frames_compared": compared, "frame_mismatches": mism}
+            compared += ref.shape[0]
+            if got.shape != ref.shape:
+                bad_streams += 1
+                mism += abs(got.shape[0] - ref.shape[0])
+            else:
+                d = int((ref != got).any(axis=1).sum())
+                mism += d
+                bad_streams += 1 if d else 0
+        spot = {"streams": cores, "frames_compared": compared, "frame_mismatches": mism, "streams_mismatching": bad_streams,
+                "compare": "whole streams (frame count and every byte)"}
 
-    # ---- channel bank (north-star target: over 16,384 concurrent streams): same chain, same timing rules
-    channel_bank = None
+    # ---- channel banks (north-star target: over 16,384 concurrent streams): same chain, same timing rules
+    channel_bank = channel_bank_strong = None
     if not args.no_bank:
         bank.close()
+        bank = None
         del bank_buf
         torch.cuda.empty_cache()
-        channel_bank = run_channel_bank(args, pkg, torch, dev, local_rank, rank, world, barrier, reduce_max_ms,
-                                        reduce_counters, peak, mb)
-        bank = None
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        Sb = args.bank_streams or 4 * 32 * sms          # 4 resident CTAs x 32 streams on every SM: 18,944 on a B200
+        channel_bank, bbank, bbuf, _ = run_bank_leg(args, pkg, torch, dev, local_rank, world, Sb, rank * Sb, args.bank_frames,
+                                                    args.bank_tiles, 20261018, barrier, reduce_max_ms, reduce_counters, peak,
+                                                    mb, "weak-scaled bank (per-GPU work fixed)")
+        channel_bank["scaling"] = "weak"
+        if not args.no_sustained:
+            bbank.close()
+            channel_bank["sustained"] = run_sustained(args, pkg, torch, np, dev, local_rank, Sb, bbuf, barrier, reduce_max_ms)
+        else:
+            bbank.close()
+        del bbuf
+        torch.cuda.empty_cache()
+        # BASELINE configs[4] as written: ONE bank of 16,384 streams split over the ranks
+        slo, shi = stream_range(rank, world, args.strong_streams)
+        channel_bank_strong, sbank, sbuf, _ = run_bank_leg(args, pkg, torch, dev, local_rank, world, shi - slo, slo,
+                                                           args.bank_frames, args.bank_tiles, 20261019, barrier, reduce_max_ms,
+                                                           reduce_counters, peak, mb,
+                                                           f"fixed {args.strong_streams}-stream bank split over {world} GPU(s)")
+        channel_bank_strong["scaling"] = "strong"
+        sbank.close()
+        del sbuf
+        torch.cuda.empty_cache()
 
     if rank == 0:
+        n_launch = (4 * len(ends) + 1) * args.steps  # est + demod + track + decode (+ log advance) per tile
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(S, args.seconds), "streams_per_gpu": S, "streams_total": S * world,
                        "frames_per_stream": n_frames, "samples_per_stream": n, "mode": "stream (-s)",
+                       "tiles_per_step": len(ends),
                        "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2; no flush needed" % (S * n * 4 / 1e9),
                        "lanes_per_stream": args.lanes},
             "frames_per_s": round(frames_per_s, 1),
@@ -462,8 +592,8 @@ def main():
             "counters": tot,
             "ber": (tot["bit_errors"] / (tot["frames_compared"] * 1072.0)) if tot["frames_compared"] else None,
             "roofline": roofline, "viterbi": viterbi, "cpu_baseline": cpu_baseline, "parity_spotcheck": spot,
-            "channel_bank": channel_bank,
-            "e2e": e2e, "gpu_launches": 5 * args.steps, "clocks": clocks,
+            "channel_bank": channel_bank, "channel_bank_strong": channel_bank_strong,
+            "e2e": e2e, "gpu_launches": n_launch, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if bank is not None:

@@ -121,7 +121,9 @@ int opvd_push_iq(opvd_handle* h, int32_t stream, const int16_t* iq, int64_t n_sa
 int opvd_push_iq_all(opvd_handle* h, const int16_t* iq, int64_t n_samples, int64_t host_stride_samples);
 /* use captures already resident in device memory: [n_streams][stride_samples] packed I/Q words.
  * d_iq must be 16-byte aligned and stride_samples a multiple of 4 (TMA bulk-copy granularity).
- * n_samples: per-stream valid lengths (host array) or NULL for n_uniform everywhere. */
+ * n_samples: per-stream valid lengths (host array) or NULL for n_uniform everywhere.  May be called again with
+ * larger lengths for the same buffer (more of the capture becomes visible: time tiles over a resident bank); after
+ * opvd_reset any lengths are accepted again. */
 int opvd_attach_device_iq(opvd_handle* h, const void* d_iq, int64_t stride_samples, const int64_t* n_samples,
                           int64_t n_uniform);
 

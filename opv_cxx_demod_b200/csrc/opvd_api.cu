@@ -419,7 +419,7 @@ int opvd_attach_device_iq(opvd_handle* h, const void* d_iq, int64_t stride_sampl
     for (int s = 0; s < h->S; ++s) {
         const int64_t n = n_samples ? n_samples[s] : n_uniform;
         if (n < 0 || n > stride_samples) return OPVD_ERR_ARG;
-        if (n < h->h_avail[s]) return OPVD_ERR_ARG;  // a stream never shrinks
+        if (n < h->h_avail[s] && h->run_seq > 0) return OPVD_ERR_ARG;  // a stream never shrinks once it has been run
     }
     for (int s = 0; s < h->S; ++s) h->h_avail[s] = n_samples ? n_samples[s] : n_uniform;
     h->d_iq = static_cast<const uint32_t*>(d_iq);

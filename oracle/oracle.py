@@ -23,6 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 REF_DEMOD = os.path.join(REF_DIR, "opv-demod")
 REF_MOD = os.path.join(REF_DIR, "opv-mod")
+REF_MODEM = os.path.join(REF_DIR, "opv-modem")
 
 SPS = 40
 FRAME_BYTES = 134
@@ -42,7 +43,8 @@ def build(force: bool = False) -> None:
     need = force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src)
     have_ref_src = os.path.exists("/root/reference/src/opv-demod.cpp")
     need_ref = have_ref_src and (force or not os.path.exists(os.path.join(REF_DIR, "libref_stages.so"))
-                                 or not os.path.exists(REF_DEMOD) or not os.path.exists(REF_MOD))
+                                 or not os.path.exists(REF_DEMOD) or not os.path.exists(REF_MOD)
+                                 or not os.path.exists(REF_MODEM))
     if need or need_ref:
         subprocess.run(["make", "-C", HERE] + (["-B"] if force else []), check=True,
                        stdout=subprocess.DEVNULL)

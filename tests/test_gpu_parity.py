@@ -425,7 +425,7 @@ def test_baseline_config_shapes_at_scale(shape, pkg, ora):
     sp = pkg.make_synth(S, n_frames, stride, n, seed=11, **kw)
     pkg.synth_bank(buf.data_ptr(), sp)
     bank = pkg.DemodBank(S, streaming=True)
-    assert bank.demod_variant() == "demod_batch_kernel"
+    assert bank.demod_variant() == "demod_bank4_kernel"
     bank.attach_device_iq(buf.data_ptr(), stride, n, keepalive=buf)
     bank.run(final=True)
     fr = bank.poll_frames()
