@@ -1,22 +1,15 @@
 // kernels_demod_bank.cu — A1/A3/A4 for sm_100a, CHANNEL-BANK variant (demod_bank_core.cuh): the kernel for
 // thousands of streams (north-star regime, >= 16,384 streams per GPU = 128 per SM).
 //
-// A CTA of 96 threads owns 32 streams; lane = stream in each of its three warps, so every instruction does 32
-// streams' worth of work and nothing is ever exchanged inside a warp.  The warps are free-running ROLES coupled only
-// by named barriers (producer/consumer hand-offs through shared memory), never by a CTA barrier:
-//   WINDOW  Horner block sums -> gate combination -> soft symbol, dominant tone -> early/late gates of the
-//           dominant tone only -> TED, timing loop, next position, call schedule (:221-286, :313, :1012-1113)
-//   AFC     phase detector, AFC loop, LO steps z (handed back first: the next symbol's Horner needs nothing else),
-//           then the LO powers z^10, z^20, zeta^40 for the gate combination (:289-310)
-//   STAGE   HBM -> transposed shared-memory ring, one batch of 32-byte sectors per lane in flight, 2-4 symbols
-//           ahead of the window; woken once per symbol by the window warp
-// The AFC chain of symbol n overlaps the early/late + timing part of symbol n.  Hardware placement (tools/warp_place.cu):
-// warp w of the j-th resident 3-warp CTA sits on SM sub-partition (3 j + w) & 3, so with four resident CTAs every
-// sub-partition hosts exactly one warp of each role.
-//
-// Two other organisations were built and measured in round 2 and lost (experiments/round2_kernels/):
-// cutting the window over two dependent warps (22.7 ms on the 18,944 x 6 probe bank) and 16 streams x 2 window halves
-// per warp with shuffles (25.4 ms), against 19.6 ms for this one.
+// A CTA owns 32 streams and keeps their samples in a transposed shared-memory ring filled by a STAGE warp.  Two
+// kernels share that machinery:
+//   * three-warp kernel (lanes_per_stream 96): lane = stream; free-running ROLE warps coupled by named barriers:
+//       WINDOW  Horner block sums -> gate combination -> soft symbol, dominant tone -> early/late gates of the
+//               dominant tone only -> TED, timing loop, next position, call schedule (:221-286, :313, :1012-1113)
+//       AFC     phase detector, AFC loop, LO steps z (handed back first), then the LO powers (:289-310)
+//       STAGE   HBM -> ring, two batches of 32-byte sectors per lane in flight, 2-4 symbols ahead of the window
+//   * half-window kernel (lanes_per_stream 128, the large-bank default): two window warps of 16 streams x 2 window
+//     halves, AFC chain in line, no hand-offs (see demod_bank16_kernel below for why).
 // Sample ring: ring[row][stream], row = sample index mod 256, rows 0..63 mirrored behind row 255 so a 61-row
 // window never wraps; lane s always reads bank s (conflict-free whatever the streams' window positions are).
 #include <cuda_runtime.h>
@@ -40,7 +33,7 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kQBias = 0x80000000u;
 
 // named barriers (0 is __syncthreads)
-enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3, kBarTick = 4 };
+enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3 };
 enum : int { kFlagTone1 = 1, kFlagFirst = 2, kFlagLive = 4, kFlagExit = 8 };
 
 struct __align__(16) BankSmem {
@@ -53,8 +46,7 @@ struct __align__(16) BankSmem {
     int fill[kSpc];               // STAGE -> WINDOW: samples [.., fill) of the stream's row are in the ring
     int live[kSpc];               // WINDOW -> STAGE: stream still has symbols to demodulate in this launch
     int exit_flag;                // WINDOW -> STAGE
-    int tick;                     // WINDOW -> STAGE: symbols started so far (the wake-up barrier's payload)
-    int stage_done;               // STAGE -> WINDOW: the staging warp has left its loop
+    int rot;                      // half-window kernel: window warps that have finished
 };
 
 template <int ID, int N>
@@ -312,33 +304,26 @@ __device__ __forceinline__ void role_stage(BankSmem& sm, int s, int stream, cons
         return can;
     };
     auto retire = [&](uint4 (&buf)[2 * NB], int& idx) {
-        if (idx >= 0) {
+        const bool had = idx >= 0;
+        if (had) {
 #pragma unroll
             for (int c = 0; c < NB; ++c) chunk_store<QX>(sm, s, idx + kChunk * c, buf[2 * c], buf[2 * c + 1]);
             __threadfence_block();
             st_vol(&sm.fill[s], idx + kBatch);
             idx = -1;
         }
+        return had;
     };
-    // One pass per symbol, woken by the window warp's tick (a named barrier: a blocked warp costs no issue slots; the
-    // first version polled the window position and spent ~670 instructions per symbol doing so, on a sub-partition
-    // it shares with another CTA's window warp).  Steady state: the batch requested at the previous tick is stored
-    // (its loads have had a whole symbol to land), the next one is requested and stays in flight until the next tick.
-    // While the ring still has room after that (start of the launch, or a stream that consumes more than 40 samples
-    // per symbol) further batches are fetched synchronously.
-    // A tick that arrives while this warp is busy is not lost: the tick counter shows it, and the pass is repeated
-    // instead of blocking.
-    int seen = 0;
     for (;;) {
-        retire(bufB, idxB);
-        request(bufB, idxB);
-        while (__any_sync(kFull, request(bufA, idxA))) retire(bufA, idxA);
-        if (ld_vol(&sm.exit_flag)) break;
-        const int t = ld_vol(&sm.tick);
-        if (t == seen) bar_sync<kBarTick, 64>();
-        seen = t;
+        bool work = request(bufA, idxA);
+        work |= retire(bufB, idxB);
+        work |= request(bufB, idxB);
+        work |= retire(bufA, idxA);
+        if (!__any_sync(kFull, work)) {
+            if (ld_vol(&sm.exit_flag)) break;
+            __nanosleep(200);
+        }
     }
-    st_vol(&sm.stage_done, 1);
     __syncthreads();  // (2)
 }
 
@@ -365,10 +350,9 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     c.init(st, sb, so, stream, valid, mode, final_flag);
     sm.w0[s] = c.w0;
     sm.live[s] = c.live ? 1 : 0;
-    if (s == 0) { sm.exit_flag = 0; sm.tick = 0; sm.stage_done = 0; }
+    if (s == 0) sm.exit_flag = 0;
     __syncthreads();  // (1) symbol 0 published
     bool any_live = __any_sync(kFull, c.live);
-    int tick = 0;
     while (any_live) {
         const bool first = c.sym_in_call == 0;
         bar_sync<kBarZ, 64>();
@@ -400,19 +384,139 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
             else st_vol(&sm.live[s], 0);
         }
         any_live = __any_sync(kFull, c.live);
-        if (any_live) {  // wake the staging warp: the window has moved on
-            st_vol(&sm.tick, ++tick);
-            bar_arrive<kBarTick, 64>();
-        }
     }
     sm.flags[s] = kFlagExit;
     st_vol(&sm.exit_flag, 1);
     bar_arrive<kBarO, 64>();
-    while (!ld_vol(&sm.stage_done)) {  // keep ticking until the staging warp has seen the exit flag
-        bar_arrive<kBarTick, 64>();
-        __nanosleep(100);
-    }
     if (valid) c.persist(st, so, dstate, stream, counters);
+    __syncthreads();  // (2)
+}
+
+// =================================================================================================================
+// Half-window kernel: two WINDOW warps + STAGE (96 threads) per 32 streams.  A window warp owns 16 streams; lane
+// sigma + 16 h holds half h of stream sigma's window:
+//   h = 0  blocks H1, H2 (slots 10..29) -> P_t,  block H0 (slots 0..9)   -> early gate
+//   h = 1  blocks H3, H4 (slots 30..49) -> R_t,  block H5 (slots 50..59) -> late gate
+// The halves swap their partial sums with 11 shuffles (xor 16) per symbol; everything that is not Horner work
+// (gate combination, soft decision, timing loop, AFC chain, LO powers) is evaluated by both lanes on identical
+// operands, so no role hand-off, named barrier or shared-memory exchange remains.  Why: with lane = stream and
+// 128 streams per SM there is ONE heavy warp per SM sub-partition, and a single in-order warp cannot hide its own
+// issue latencies (2.7 cycles per instruction in every phase, FP64 pipe 46 % busy, profiles/ncu_bank_r02_a_roles.txt);
+// cutting the window over two DEPENDENT warps only time-shares the sub-partition (profiles/ncu_bank4_r02_b_roles.txt).
+// Here every sub-partition runs two INDEPENDENT heavy warps (different CTAs) on the same 128 streams per SM, for
+// ~18 % more FP64 instructions.  The arithmetic is the four-warp decomposition of demod_bank_core.cuh, bit for bit.
+// (Hardware placement, tools/warp_place.cu: warp w of the j-th resident 3-warp CTA sits on sub-partition
+// (3 j + w) & 3, so the two window warps of four resident CTAs cover every sub-partition exactly twice.)
+__device__ __forceinline__ cplx shfl_x16(cplx v) {
+    return {__shfl_xor_sync(kFull, v.r, 16), __shfl_xor_sync(kFull, v.i, 16)};
+}
+__device__ __forceinline__ cplx csel(bool p, cplx a, cplx b) { return p ? a : b; }
+
+template <int QX>
+__global__ void __launch_bounds__(96, 4)
+demod_bank16_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
+                    int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BankSmem& sm = *reinterpret_cast<BankSmem*>(smem_raw);
+    const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { sm.exit_flag = 0; sm.rot = 0; }  // rot counts the window warps that have finished
+    if (role == 2) {
+        const int stream_raw = blockIdx.x * kSpc + lane;
+        role_stage<QX, 5>(sm, lane, stream_raw < n_streams ? stream_raw : n_streams - 1, sb, dstate);
+        return;
+    }
+    const int h = lane >> 4, s = 16 * role + (lane & 15);  // half, CTA-local stream
+    const bool hi = h != 0;
+    const int stream_raw = blockIdx.x * kSpc + s;
+    const bool valid = stream_raw < n_streams;
+    const int stream = valid ? stream_raw : n_streams - 1;
+
+    DemodState st = dstate[stream];  // local memory: only the scheduler touches it (both halves keep a copy)
+    BankAfc afc = {st.freq_offset, st.ph1, st.ph2, st.p1, st.p2};
+    BankLo lo;
+    BankPow pw;
+    {
+        double d;
+        const cplx zeta = bank_zeta_general(afc.freq_offset, d);  // a -o offset may exceed the fast range
+        bank_lo_from_zeta(zeta, d, lo, g_fm);
+        bank_pow_from_zeta(zeta, pw, g_bk);
+    }
+    WindowCtl c;
+    c.init(st, sb, so, stream, valid, mode, final_flag);
+    // the stream's record is written once, by half 0, at the moment the stream ends for this launch (or here when it
+    // has nothing to do), so the hot loop can update its state in place without selects for finished lanes
+    auto persist = [&](const BankAfc& a) {
+        if (valid && !hi) {
+            c.persist(st, so, dstate, stream, counters);
+            DemodState* d = dstate + stream;
+            d->freq_offset = a.freq_offset; d->ph1 = a.ph1; d->ph2 = a.ph2; d->p1 = a.p1; d->p2 = a.p2;
+        }
+        if (!hi) st_vol(&sm.live[s], 0);
+    };
+    if (!hi) {
+        sm.w0[s] = c.w0;
+        sm.live[s] = c.live ? 1 : 0;
+    }
+    if (!c.live) persist(afc);
+    __syncthreads();  // (1) symbol 0 published
+    bool any_live = __any_sync(kFull, c.live);
+    while (any_live) {
+        const bool first = c.sym_in_call == 0;
+        wait_window(sm, s, c.live, c.w0);
+        const uint32_t* const win = &sm.ring[c.w0 & (kRingRows - 1)][s];
+        const uint32_t* const won = win + (10 + 20 * h) * kSpc;  // this half's on-time blocks: slots 10+20h .. 29+20h
+        const uint32_t* const wel = win + 50 * h * kSpc;         // early (slots 0..9) / late (slots 50..59) block
+        auto slot_on = [&](int k, double& I, double& Q) { unpack_ring<QX>(won[k * kSpc], k, I, Q); };
+        auto slot_el = [&](int k, double& I, double& Q) { unpack_ring<QX>(wel[k * kSpc], k, I, Q); };
+        // ---- on-time half: two blocks, both tones
+        cplx A[2], B[2], f0, f1, x0;
+        bank_two_blocks(slot_on, 0, lo.z1, lo.z2, A, B, f0, f1);
+        slot_el(0, x0.r, x0.i);  // slot 0 (h = 0) / slot 50 (h = 1)
+        const cplx Y1 = cfma(pw.q1, A[1], A[0]), Y2 = cfma(pw.q2, B[1], B[0]);  // P_t (h = 0) / R_t (h = 1)
+        const cplx Z1 = shfl_x16(Y1), Z2 = shfl_x16(Y2);
+        const cplx v = shfl_x16(csel(hi, x0, f0));
+        const cplx s10 = csel(hi, v, f0), s50 = csel(hi, x0, v);
+        cplx O1, O2;
+        double eO1, eO2;
+        bank_on_time_from_halves(c.f, lo, pw, csel(hi, Z1, Y1), csel(hi, Z2, Y2), csel(hi, Y1, Z1), csel(hi, Y2, Z2), s10, s50,
+                                 O1, O2, eO1, eO2);
+        const bool tone1 = eO1 > eO2;  // :272, :291
+        if (c.live && !hi) c.put_soft(eO2 - eO1);
+        // ---- what the early / late gate needs of this symbol's LO (the AFC chain below replaces lo and pw in place)
+        const cplx zd = tone1 ? lo.z1 : lo.z2, qd = tone1 ? pw.q1 : pw.q2, qqd = tone1 ? pw.qq1 : pw.qq2;
+        const cplx z40d = bank_z40(pw.zeta40, tone1 ? 0 : 1);
+        // ---- AFC chain and the LO steps of the next symbol, in place (independent of the early/late work, so the
+        // two interleave; a lane whose stream has ended keeps computing on stale operands: its record was written when
+        // it ended)
+        bank_afc(afc, O1, O2, tone1, pw.zeta40, lo.inc1, lo.inc2, first, afc_alpha, g_fm);
+        if (!first) {  // no AFC update on the first symbol of a call (:289): same LO steps next symbol
+            double d;
+            const cplx zeta = bank_zeta_fast(afc.freq_offset, d, g_fm);  // |offset| <= 2 kHz after the clamp (:303)
+            bank_lo_from_zeta(zeta, d, lo, g_fm);
+            bank_pow_from_zeta(zeta, pw, g_bk);
+        }
+        // ---- early (h = 0) / late (h = 1) gate of the dominant tone
+        const cplx recvH = shfl_x16(hi ? (tone1 ? A[0] : B[0]) : (tone1 ? A[1] : B[1]));  // H3 to h = 0, H2 to h = 1
+        const cplx recvf = shfl_x16(f1);                                                  // s40 to h = 0, s20 to h = 1
+        cplx fixE = {0.0, 0.0};
+        if (first && c.live && !hi) fixE = first_fix_cold<QX>(win, c.f, zd);  // :237, once per call
+        cplx HEL, e0, x1;
+        bank_block_one(slot_el, 0, zd, HEL, e0);
+        slot_el(10, x1.r, x1.i);  // slot 60 (h = 1)
+        const double e = bank_gate_energy(c.f, zd, qd, qqd, z40d, csel(hi, recvH, HEL), tone1 ? Y1 : Y2, csel(hi, HEL, recvH),
+                                          csel(hi, x1, recvf), csel(hi, recvf, x0), fixE);
+        const double er = __shfl_xor_sync(kFull, e, 16);
+        const double eE = hi ? er : e, eL = hi ? e : er;
+        // ---- timing loop, next symbol
+        if (c.live) {
+            bank_timing(eE, eL, c.timing_freq, c.pos, g_fm);
+            c.advance(st, mode, final_flag);
+            if (!c.live) persist(afc);  // the stream has ended for this launch
+            else if (!hi) st_vol(&sm.w0[s], c.w0);
+        }
+        any_live = __any_sync(kFull, c.live);
+    }
+    if (lane == 0 && atomicAdd(&sm.rot, 1) == 1) st_vol(&sm.exit_flag, 1);  // both window warps done: stop the staging warp
     __syncthreads();  // (2)
 }
 
@@ -426,6 +530,17 @@ static cudaError_t launch_bank_t(const StreamBuffers& sb, const SoftBuffers& so,
     demod_bank_kernel<QX><<<grid, 96, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
     return cudaGetLastError();
 }
+template <int QX>
+static cudaError_t launch_bank16_t(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams, int mode,
+                                   int final_flag, double afc_alpha, unsigned long long* counters, cudaStream_t st) {
+    const size_t smem = sizeof(BankSmem);
+    cudaError_t e = cudaFuncSetAttribute(demod_bank16_kernel<QX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (n_streams + kSpc - 1) / kSpc;
+    demod_bank16_kernel<QX><<<grid, 96, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
+    return cudaGetLastError();
+}
+
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -439,6 +554,15 @@ cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, De
     if (qx == 0) return launch_bank_t<0>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     if (qx == 2) return launch_bank_t<2>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     return launch_bank_t<1>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+}
+
+cudaError_t launch_demod_bank4(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
+                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
+                               cudaStream_t st) {
+    static const int qx = env_int("OPVD_BANK_QX", 2);
+    if (qx == 0) return launch_bank16_t<0>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    if (qx == 1) return launch_bank16_t<1>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    return launch_bank16_t<2>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
 }
 
 }  // namespace opvd

@@ -1,22 +1,23 @@
 // kernels_demod_bank.cu — A1/A3/A4 for sm_100a, CHANNEL-BANK variant (demod_bank_core.cuh): the kernel for
 // thousands of streams (north-star regime, >= 16,384 streams per GPU = 128 per SM).
 //
-// A CTA of 96 threads owns 32 streams; lane = stream in each of its three warps, so every instruction does 32
-// streams' worth of work and nothing is ever exchanged inside a warp.  The warps are free-running ROLES coupled only
-// by named barriers (producer/consumer hand-offs through shared memory), never by a CTA barrier:
+// A CTA owns 32 streams; lane = stream in every warp, so every instruction does 32 streams' worth of work and
+// nothing is ever exchanged inside a warp.  The warps are free-running ROLES coupled only by named barriers
+// (producer/consumer hand-offs through shared memory), never by a CTA barrier:
 //   WINDOW  Horner block sums -> gate combination -> soft symbol, dominant tone -> early/late gates of the
-//           dominant tone only -> TED, timing loop, next position, call schedule (:221-286, :313, :1012-1113)
+//           dominant tone only -> TED, timing loop, next position, call schedule (:221-286, :313, :1012-1113).
+//           In the four-warp kernel the window is cut in two halves that run as two warps (LO: blocks H1, H2, H0,
+//           on-time combination, early gate, timing loop; HI: blocks H3, H4, H5, late gate): one warp per SM
+//           sub-partition cannot hide its own issue latencies (measured: 2.9 cycles per instruction, FP64 pipe
+//           46 % busy with the single window warp of the three-warp kernel, profiles/ncu_bank_r02_a_roles.txt).
 //   AFC     phase detector, AFC loop, LO steps z (handed back first: the next symbol's Horner needs nothing else),
 //           then the LO powers z^10, z^20, zeta^40 for the gate combination (:289-310)
-//   STAGE   HBM -> transposed shared-memory ring, one batch of 32-byte sectors per lane in flight, 2-4 symbols
-//           ahead of the window; woken once per symbol by the window warp
-// The AFC chain of symbol n overlaps the early/late + timing part of symbol n.  Hardware placement (tools/warp_place.cu):
-// warp w of the j-th resident 3-warp CTA sits on SM sub-partition (3 j + w) & 3, so with four resident CTAs every
-// sub-partition hosts exactly one warp of each role.
+//   STAGE   moves the streams' samples from HBM into the transposed shared-memory ring, two batches of 32-byte
+//           sectors per lane in flight, 2-4 symbols ahead of the window (flow control through two per-stream words
+//           in shared memory, no barrier)
+// The AFC chain of symbol n overlaps the early/late + timing part of symbol n, and the FP64 pipe — the unit that
+// bounds this kernel — always sees several independent instruction streams.
 //
-// Two other organisations were built and measured in round 2 and lost (experiments/round2_kernels/):
-// cutting the window over two dependent warps (22.7 ms on the 18,944 x 6 probe bank) and 16 streams x 2 window halves
-// per warp with shuffles (25.4 ms), against 19.6 ms for this one.
 // Sample ring: ring[row][stream], row = sample index mod 256, rows 0..63 mirrored behind row 255 so a 61-row
 // window never wraps; lane s always reads bank s (conflict-free whatever the streams' window positions are).
 #include <cuda_runtime.h>
@@ -40,7 +41,7 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kQBias = 0x80000000u;
 
 // named barriers (0 is __syncthreads)
-enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3, kBarTick = 4 };
+enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3, kBarX1 = 4, kBarX2 = 5, kBarX3 = 6, kBarX4 = 7 };
 enum : int { kFlagTone1 = 1, kFlagFirst = 2, kFlagLive = 4, kFlagExit = 8 };
 
 struct __align__(16) BankSmem {
@@ -48,13 +49,19 @@ struct __align__(16) BankSmem {
     double o[4][kSpc];            // WINDOW -> AFC: O1.r, O1.i, O2.r, O2.i
     double z[4][kSpc];            // AFC -> WINDOW: z1.r, z1.i, z2.r, z2.i
     double pw[10][kSpc];          // AFC -> WINDOW: q1, q2, qq1, qq2, zeta40
+    double x1[12][kSpc];          // HI -> LO: R1, R2, H3 (F1), H3 (F2), s40, s50
+    double x2[4][kSpc];           // LO -> HI: H2 of the dominant tone, s20
+    double x3[kSpc];              // HI -> LO: late-gate energy
+    double x4f[kSpc];             // LO -> HI: interpolation fraction of the next symbol
+    int x4w[kSpc];                // LO -> HI: window start of the next symbol
+    int x4flags[kSpc];            // LO -> HI: kFlagLive / kFlagExit for the next symbol
+    int x2flags[kSpc];            // LO -> HI: kFlagTone1
     int flags[kSpc];              // WINDOW -> AFC: kFlag*
     int w0[kSpc];                 // WINDOW -> STAGE: row-relative sample index of window slot 0 of the current symbol
     int fill[kSpc];               // STAGE -> WINDOW: samples [.., fill) of the stream's row are in the ring
     int live[kSpc];               // WINDOW -> STAGE: stream still has symbols to demodulate in this launch
     int exit_flag;                // WINDOW -> STAGE
-    int tick;                     // WINDOW -> STAGE: symbols started so far (the wake-up barrier's payload)
-    int stage_done;               // STAGE -> WINDOW: the staging warp has left its loop
+    int rot;                      // role rotation of this CTA (four-warp kernel)
 };
 
 template <int ID, int N>
@@ -312,33 +319,26 @@ __device__ __forceinline__ void role_stage(BankSmem& sm, int s, int stream, cons
         return can;
     };
     auto retire = [&](uint4 (&buf)[2 * NB], int& idx) {
-        if (idx >= 0) {
+        const bool had = idx >= 0;
+        if (had) {
 #pragma unroll
             for (int c = 0; c < NB; ++c) chunk_store<QX>(sm, s, idx + kChunk * c, buf[2 * c], buf[2 * c + 1]);
             __threadfence_block();
             st_vol(&sm.fill[s], idx + kBatch);
             idx = -1;
         }
+        return had;
     };
-    // One pass per symbol, woken by the window warp's tick (a named barrier: a blocked warp costs no issue slots; the
-    // first version polled the window position and spent ~670 instructions per symbol doing so, on a sub-partition
-    // it shares with another CTA's window warp).  Steady state: the batch requested at the previous tick is stored
-    // (its loads have had a whole symbol to land), the next one is requested and stays in flight until the next tick.
-    // While the ring still has room after that (start of the launch, or a stream that consumes more than 40 samples
-    // per symbol) further batches are fetched synchronously.
-    // A tick that arrives while this warp is busy is not lost: the tick counter shows it, and the pass is repeated
-    // instead of blocking.
-    int seen = 0;
     for (;;) {
-        retire(bufB, idxB);
-        request(bufB, idxB);
-        while (__any_sync(kFull, request(bufA, idxA))) retire(bufA, idxA);
-        if (ld_vol(&sm.exit_flag)) break;
-        const int t = ld_vol(&sm.tick);
-        if (t == seen) bar_sync<kBarTick, 64>();
-        seen = t;
+        bool work = request(bufA, idxA);
+        work |= retire(bufB, idxB);
+        work |= request(bufB, idxB);
+        work |= retire(bufA, idxA);
+        if (!__any_sync(kFull, work)) {
+            if (ld_vol(&sm.exit_flag)) break;
+            __nanosleep(200);
+        }
     }
-    st_vol(&sm.stage_done, 1);
     __syncthreads();  // (2)
 }
 
@@ -365,10 +365,9 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     c.init(st, sb, so, stream, valid, mode, final_flag);
     sm.w0[s] = c.w0;
     sm.live[s] = c.live ? 1 : 0;
-    if (s == 0) { sm.exit_flag = 0; sm.tick = 0; sm.stage_done = 0; }
+    if (s == 0) sm.exit_flag = 0;
     __syncthreads();  // (1) symbol 0 published
     bool any_live = __any_sync(kFull, c.live);
-    int tick = 0;
     while (any_live) {
         const bool first = c.sym_in_call == 0;
         bar_sync<kBarZ, 64>();
@@ -400,20 +399,161 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
             else st_vol(&sm.live[s], 0);
         }
         any_live = __any_sync(kFull, c.live);
-        if (any_live) {  // wake the staging warp: the window has moved on
-            st_vol(&sm.tick, ++tick);
-            bar_arrive<kBarTick, 64>();
-        }
     }
     sm.flags[s] = kFlagExit;
     st_vol(&sm.exit_flag, 1);
     bar_arrive<kBarO, 64>();
-    while (!ld_vol(&sm.stage_done)) {  // keep ticking until the staging warp has seen the exit flag
-        bar_arrive<kBarTick, 64>();
-        __nanosleep(100);
-    }
     if (valid) c.persist(st, so, dstate, stream, counters);
     __syncthreads();  // (2)
+}
+
+// =================================================================================================================
+// Four-warp kernel: WINDOW-LO, WINDOW-HI, AFC, STAGE (128 threads).  Roles rotate with the CTA's arrival order on
+// its SM so that the four resident CTAs put one warp of every role on each SM sub-partition.
+__device__ int g_sm_arrivals[1024];
+
+template <int QX>
+__global__ void __launch_bounds__(128, 4)
+demod_bank4_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
+                   int final_flag, double afc_alpha, int rotate, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BankSmem& sm = *reinterpret_cast<BankSmem*>(smem_raw);
+    if (threadIdx.x == 0) {
+        int rot = 0;
+        if (rotate) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            rot = atomicAdd(&g_sm_arrivals[smid & 1023], 1) & 3;
+        }
+        sm.rot = rot;
+        sm.exit_flag = 0;
+    }
+    __syncthreads();  // (0)
+    const int s = threadIdx.x & 31, role = ((threadIdx.x >> 5) + sm.rot) & 3;
+    const int stream_raw = blockIdx.x * kSpc + s;
+    const bool valid = stream_raw < n_streams;
+    const int stream = valid ? stream_raw : n_streams - 1;
+
+    if (role == 2) { role_afc<96>(sm, s, stream, valid, dstate, afc_alpha); return; }
+    if (role == 3) { role_stage<QX, 4>(sm, s, stream, sb, dstate); return; }
+
+    if (role == 0) {
+        // ============================================================= WINDOW-LO: H1, H2, on-time, H0, early, timing
+        DemodState st = dstate[stream];  // local memory: only the scheduler touches it
+        WindowCtl c;
+        c.init(st, sb, so, stream, valid, mode, final_flag);
+        sm.w0[s] = c.w0;
+        sm.live[s] = c.live ? 1 : 0;
+        sm.x4w[s] = c.w0; sm.x4f[s] = c.f; sm.x4flags[s] = c.live ? kFlagLive : 0;
+        __syncthreads();  // (1) symbol 0 published
+        bool any_live = __any_sync(kFull, c.live);
+        while (any_live) {
+            const bool first = c.sym_in_call == 0;
+            bar_sync<kBarZ, 96>();
+            BankLo lo;
+            load_lo(sm, s, lo);
+            wait_window(sm, s, c.live, c.w0);
+            const uint32_t* const win = &sm.ring[c.w0 & (kRingRows - 1)][s];
+            auto slot = [&](int k, double& I, double& Q) { unpack_ring<QX>(win[k * kSpc], k, I, Q); };
+            cplx A[2], B[2], s10, s20;
+            bank_two_blocks(slot, 10, lo.z1, lo.z2, A, B, s10, s20);
+            bar_sync<kBarPow, 96>();
+            BankPow pw;
+            load_pow(sm, s, pw);
+            const cplx P1 = cfma(pw.q1, A[1], A[0]), P2 = cfma(pw.q2, B[1], B[0]);
+            // ---- the HI warp's half
+            bar_sync<kBarX1, 64>();
+            const cplx R1 = {sm.x1[0][s], sm.x1[1][s]}, R2 = {sm.x1[2][s], sm.x1[3][s]};
+            const cplx s50 = {sm.x1[10][s], sm.x1[11][s]};
+            cplx O1, O2;
+            double eO1, eO2;
+            bank_on_time_from_halves(c.f, lo, pw, P1, P2, R1, R2, s10, s50, O1, O2, eO1, eO2);
+            const bool tone1 = eO1 > eO2;  // :272, :291
+            sm.o[0][s] = O1.r; sm.o[1][s] = O1.i; sm.o[2][s] = O2.r; sm.o[3][s] = O2.i;
+            sm.flags[s] = (tone1 ? kFlagTone1 : 0) | (first ? kFlagFirst : 0) | (c.live ? kFlagLive : 0);
+            bar_arrive<kBarO, 64>();  // the AFC warp takes it from here
+            {
+                const cplx H2 = tone1 ? A[1] : B[1];
+                sm.x2[0][s] = H2.r; sm.x2[1][s] = H2.i; sm.x2[2][s] = s20.r; sm.x2[3][s] = s20.i;
+                sm.x2flags[s] = tone1 ? kFlagTone1 : 0;
+            }
+            bar_arrive<kBarX2, 64>();  // the HI warp can finish the late gate
+            if (c.live) c.put_soft(eO2 - eO1);
+            // ---- early gate of the dominant tone
+            const cplx zd = tone1 ? lo.z1 : lo.z2;
+            cplx fixE = {0.0, 0.0};
+            if (first && c.live) fixE = first_fix_cold<QX>(win, c.f, zd);  // :237, once per call
+            cplx H0, s0;
+            bank_block_one(slot, 0, zd, H0, s0);
+            const cplx H3 = tone1 ? cplx{sm.x1[4][s], sm.x1[5][s]} : cplx{sm.x1[6][s], sm.x1[7][s]};
+            const cplx s40 = {sm.x1[8][s], sm.x1[9][s]};
+            const double eE = bank_gate_energy(c.f, zd, tone1 ? pw.q1 : pw.q2, tone1 ? pw.qq1 : pw.qq2,
+                                               bank_z40(pw.zeta40, tone1 ? 0 : 1), H0, tone1 ? P1 : P2, H3, s40, s0, fixE);
+            bar_sync<kBarX3, 64>();
+            const double eL = sm.x3[s];
+            if (c.live) {
+                bank_timing(eE, eL, c.timing_freq, c.pos, g_fm);
+                c.advance(st, mode, final_flag);
+                if (c.live) st_vol(&sm.w0[s], c.w0);
+                else st_vol(&sm.live[s], 0);
+            }
+            any_live = __any_sync(kFull, c.live);
+            sm.x4w[s] = c.w0; sm.x4f[s] = c.f;
+            sm.x4flags[s] = (c.live ? kFlagLive : 0) | (any_live ? 0 : kFlagExit);
+            bar_arrive<kBarX4, 64>();
+        }
+        sm.flags[s] = kFlagExit;
+        st_vol(&sm.exit_flag, 1);
+        bar_arrive<kBarO, 64>();
+        if (valid) c.persist(st, so, dstate, stream, counters);
+        __syncthreads();  // (2)
+    } else {
+        // ============================================================= WINDOW-HI: H3, H4, H5 (both tones), late gate
+        __syncthreads();  // (1)
+        int w0 = sm.x4w[s];
+        double f = sm.x4f[s];
+        int fl = sm.x4flags[s];
+        bool any_live = __any_sync(kFull, (fl & kFlagLive) != 0);
+        while (any_live) {
+            const bool live = (fl & kFlagLive) != 0;
+            bar_sync<kBarZ, 96>();
+            BankLo lo;
+            load_lo(sm, s, lo);
+            wait_window(sm, s, live, w0);
+            const uint32_t* const win = &sm.ring[w0 & (kRingRows - 1)][s];
+            auto slot = [&](int k, double& I, double& Q) { unpack_ring<QX>(win[k * kSpc], k, I, Q); };
+            cplx C[2], D[2], s30, s40, s50;
+            bank_two_blocks(slot, 30, lo.z1, lo.z2, C, D, s30, s40);
+            slot(50, s50.r, s50.i);
+            bar_sync<kBarPow, 96>();
+            BankPow pw;
+            load_pow(sm, s, pw);
+            const cplx R1 = cfma(pw.q1, C[1], C[0]), R2 = cfma(pw.q2, D[1], D[0]);
+            sm.x1[0][s] = R1.r; sm.x1[1][s] = R1.i; sm.x1[2][s] = R2.r; sm.x1[3][s] = R2.i;
+            sm.x1[4][s] = C[0].r; sm.x1[5][s] = C[0].i; sm.x1[6][s] = D[0].r; sm.x1[7][s] = D[0].i;
+            sm.x1[8][s] = s40.r; sm.x1[9][s] = s40.i; sm.x1[10][s] = s50.r; sm.x1[11][s] = s50.i;
+            bar_arrive<kBarX1, 64>();
+            // ---- H5 of both tones while the LO warp decides the dominant tone
+            cplx H5a, H5b, s60;
+            bank_block_both(slot, 50, lo.z1, lo.z2, H5a, H5b);
+            slot(60, s60.r, s60.i);
+            bar_sync<kBarX2, 64>();
+            const bool tone1 = (sm.x2flags[s] & kFlagTone1) != 0;
+            const cplx H2 = {sm.x2[0][s], sm.x2[1][s]}, s20 = {sm.x2[2][s], sm.x2[3][s]};
+            const double eL = bank_gate_energy(f, tone1 ? lo.z1 : lo.z2, tone1 ? pw.q1 : pw.q2, tone1 ? pw.qq1 : pw.qq2,
+                                               bank_z40(pw.zeta40, tone1 ? 0 : 1), H2, tone1 ? R1 : R2, tone1 ? H5a : H5b,
+                                               s60, s20, cplx{0.0, 0.0});
+            sm.x3[s] = eL;
+            bar_arrive<kBarX3, 64>();
+            // ---- next symbol
+            bar_sync<kBarX4, 64>();
+            w0 = sm.x4w[s];
+            f = sm.x4f[s];
+            fl = sm.x4flags[s];
+            any_live = !(fl & kFlagExit);  // warp-uniform: the LO warp sets it on every lane
+        }
+        __syncthreads();  // (2)
+    }
 }
 
 template <int QX>
@@ -426,12 +566,23 @@ static cudaError_t launch_bank_t(const StreamBuffers& sb, const SoftBuffers& so,
     demod_bank_kernel<QX><<<grid, 96, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
     return cudaGetLastError();
 }
+template <int QX>
+static cudaError_t launch_bank4_t(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams, int mode,
+                                  int final_flag, double afc_alpha, int rotate, unsigned long long* counters, cudaStream_t st) {
+    const size_t smem = sizeof(BankSmem);
+    cudaError_t e = cudaFuncSetAttribute(demod_bank4_kernel<QX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (n_streams + kSpc - 1) / kSpc;
+    demod_bank4_kernel<QX><<<grid, 128, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, rotate, counters);
+    return cudaGetLastError();
+}
+
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
 }
 
-// OPVD_BANK_QX: development switch (conversion split); results are identical
+// OPVD_BANK_QX / OPVD_BANK_ROTATE: development switches (conversion split, role rotation); results are identical
 cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                               cudaStream_t st) {
@@ -439,6 +590,15 @@ cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, De
     if (qx == 0) return launch_bank_t<0>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     if (qx == 2) return launch_bank_t<2>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     return launch_bank_t<1>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+}
+
+cudaError_t launch_demod_bank4(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
+                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
+                               cudaStream_t st) {
+    static const int qx = env_int("OPVD_BANK_QX", 2), rotate = env_int("OPVD_BANK_ROTATE", 1);
+    if (qx == 0) return launch_bank4_t<0>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, rotate, counters, st);
+    if (qx == 1) return launch_bank4_t<1>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, rotate, counters, st);
+    return launch_bank4_t<2>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, rotate, counters, st);
 }
 
 }  // namespace opvd

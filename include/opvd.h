@@ -58,8 +58,8 @@ typedef struct opvd_config {
     int32_t max_frames;        /* frames per stream that may wait between two polls (the device frame log holds
                                   n_streams * max_frames entries); 0 = derived */
     int32_t lanes_per_stream;  /* demodulator kernel variant: 0 = chosen from n_streams; 32 = one warp per stream (small
-                                  banks, lowest per-symbol latency); 96 / 128 = channel-bank kernel, 32 streams per CTA
-                                  with three / four role warps (large banks; 128 is what 0 selects for them) */
+                                  banks, lowest per-symbol latency); 96 = channel-bank kernel, 32 streams per CTA with
+                                  three role warps (large banks) */
     int32_t coherent;          /* -c: CoherentMSKDemodulator (:365-572) instead of MSKDemodulatorAFC; honoured in batch
                                   mode only, like the reference (the streaming branch returns first, :995-1125) */
     int32_t reserved0;

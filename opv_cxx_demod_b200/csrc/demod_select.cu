@@ -4,8 +4,7 @@
 // parallel axes are streams and the inside of one symbol, and the fastest organisation depends on how many streams
 // there are per SM:
 //   lanes_per_stream = 32   one warp per stream (kernels_demod_warp.cu): lowest per-symbol latency, for small banks
-//   lanes_per_stream = 96   channel-bank kernel, three role warps per 32 streams (kernels_demod_bank.cu)
-//   lanes_per_stream = 128  channel-bank kernel, four role warps per 32 streams: the large-bank default
+//   lanes_per_stream = 96   channel-bank kernel, three role warps per 32 streams (kernels_demod_bank.cu): large banks
 #include <cuda_runtime.h>
 
 #include "opvd_kernels.cuh"
@@ -18,7 +17,7 @@ int demod_auto_lanes(int n_streams) {
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if ((long long)n_streams <= 16ll * sms) return 32;
-    return 128;
+    return 96;
 }
 
 cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
@@ -26,7 +25,6 @@ cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodSt
                          unsigned long long* counters, cudaStream_t st) {
     if (n_streams <= 0) return cudaSuccess;
     const int L = lanes_per_stream > 0 ? lanes_per_stream : demod_auto_lanes(n_streams);
-    if (L >= 128) return launch_demod_bank4(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     if (L >= 96) return launch_demod_bank(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     return launch_demod_warp(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
 }

@@ -106,9 +106,8 @@ __device__ __forceinline__ long long soft_pos(const SoftBuffers& so, long long n
 void launch_estimate(const StreamBuffers& sb, DemodState* dstate, double* est_out, int n_streams, int mode,
                      int final_flag, cudaStream_t st);
 
-// lanes_per_stream in {32, 96, 128}; 0 = chosen from the stream count (demod_select.cu); returns cudaError
-//   32   warp per stream (kernels_demod_warp.cu)
-//   96   channel bank, three role warps per 32 streams      128  four role warps (kernels_demod_bank.cu)
+// lanes_per_stream in {32, 96}; 0 = chosen from the stream count (demod_select.cu); returns cudaError
+//   32   warp per stream (kernels_demod_warp.cu)      96   channel bank, three role warps per 32 streams
 cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                          int mode, int final_flag, double afc_alpha, int lanes_per_stream,
                          unsigned long long* counters, cudaStream_t st);
@@ -126,11 +125,6 @@ cudaError_t launch_demod_warp(const StreamBuffers& sb, const SoftBuffers& so, De
 cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                               cudaStream_t st);
-
-// four-warp channel-bank variant (two window warps per 32 streams); lanes_per_stream == 128
-cudaError_t launch_demod_bank4(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
-                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
-                               cudaStream_t st);
 
 // coherent mode (kernels_demod_coherent.cu): `opv-demod -c`, batch only
 cudaError_t launch_demod_coherent(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,

@@ -131,7 +131,7 @@ class DemodBank:
     def demod_variant(self) -> str:
         """Name of the demodulator kernel this bank runs (automatic selection resolved)."""
         lanes = int(self._lib.opvd_demod_lanes(self._h))
-        return {32: "demod_warp_kernel", 96: "demod_bank_kernel", 128: "demod_bank4_kernel"}.get(
+        return {32: "demod_warp_kernel", 96: "demod_bank_kernel"}.get(
             lanes, f"demod(lanes={lanes})")
 
     # -- output --------------------------------------------------------------------------------
