@@ -130,7 +130,8 @@ bool gather(const Options& o, Shard& sh, std::vector<Source>& src, int timeout_m
         Source& s = src[(size_t)(sh.first + k)];
         if (s.eof) continue;
         all_eof = false;
-        if ((int64_t)s.stage.size() >= o.tile * 4) continue;  // this stream's tile is full: push first
+        // this stream's tile is full: push first (a datagram must fit whole, or recv would truncate it)
+        if ((int64_t)s.stage.size() + (s.is_udp ? 65536 : 1) > o.tile * 4) continue;
         pf.push_back({s.fd, POLLIN, 0});
         who.push_back(sh.first + k);
     }

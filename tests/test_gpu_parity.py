@@ -264,6 +264,75 @@ def test_bank_cli_matches_per_stream_reference(flags, pkg, cases, ora, tmp_path)
     assert p.returncode == 1 and p.stderr == b""
 
 
+def test_bank_cli_live_fifo_ingest_and_shards(pkg, cases, ora, tmp_path):
+    """opv-demod-bank -s fed through FIFOs by writers that trickle bytes at different paces (live ingest: every stream
+    advances with what it has, the staging remainder of a split sample stays on the host), sharded over two library
+    handles (`--devices`: two GPUs when the box has them, twice the same GPU otherwise; the per-shard counters are
+    summed by NCCL or, with a duplicate device, on the host).  Per stream the frames equal the reference's stdout."""
+    import threading
+
+    import torch
+
+    names = ["clean5", "awgn8", "cfo_p1200_delay", "short_lt_chunk", "clean12_call"]
+    fifos = []
+    for k, name in enumerate(names):
+        f = tmp_path / f"{k}_{name}.fifo"
+        os.mkfifo(f)
+        fifos.append(str(f))
+    out = tmp_path / "out"
+    out.mkdir()
+    devs = "0,1" if torch.cuda.device_count() >= 2 else "0,0"
+    proc = subprocess.Popen([pkg.BANK_CLI_PATH, "-s", "--devices", devs, "--tile", "86720", "-d", str(out), *fifos],
+                            stderr=subprocess.PIPE)
+
+    def feed(path, data, step):
+        with open(path, "wb", buffering=0) as w:
+            for pos in range(0, len(data), step):
+                w.write(data[pos:pos + step])
+
+    th = []
+    for k, name in enumerate(names):
+        data = np.ascontiguousarray(cases[name]).tobytes()
+        th.append(threading.Thread(target=feed, args=(fifos[k], data, 30001 + 7777 * k)))  # odd sizes: samples get split
+        th[-1].start()
+    for t in th:
+        t.join()
+    err = proc.communicate(timeout=120)[1]
+    assert proc.returncode == 0, err.decode("utf8", "replace")[-600:]
+    total = 0
+    for k, name in enumerate(names):
+        got = open(out / f"{k}_{name}.fifo.frames", "rb").read()
+        assert hashlib.sha256(got).hexdigest() == GOLD[f"{name}/stream"]["frames_sha256"], name
+        total += len(got) // 134
+    assert f"Summary: {len(names)} streams, {total} frames".encode() in err
+    assert f"frames decoded {total},".encode() in err          # the reduced device counters agree with the frame files
+
+
+def test_bank_cli_udp_ingest(pkg, cases, tmp_path):
+    """opv-demod-bank --udp-in PORT --streams N: every stream receives its samples as UDP datagrams (one receiver per
+    port, where N x `... | opv-modem -R` sit today); it stops after --idle-exit seconds without traffic."""
+    import socket
+    import time
+
+    names = ["clean5", "awgn8"]
+    base = 42000 + os.getpid() % 1000
+    proc = subprocess.Popen([pkg.BANK_CLI_PATH, "-s", "-q", "--udp-in", str(base), "--streams", str(len(names)),
+                             "--idle-exit", "3", "-d", str(tmp_path)], stderr=subprocess.PIPE)
+    time.sleep(4.0)  # CUDA start-up; datagrams sent before the sockets exist would be lost
+    tx = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    for k, name in enumerate(names):
+        data = np.ascontiguousarray(cases[name]).tobytes()
+        for pos in range(0, len(data), 8192):
+            tx.sendto(data[pos:pos + 8192], ("127.0.0.1", base + k))
+            if (pos // 8192) % 64 == 63:
+                time.sleep(0.002)  # stay below the receive buffer
+    err = proc.communicate(timeout=120)[1]
+    assert proc.returncode == 0, err.decode("utf8", "replace")[-400:]
+    for k, name in enumerate(names):
+        got = open(tmp_path / f"udp{k}.frames", "rb").read()
+        assert hashlib.sha256(got).hexdigest() == GOLD[f"{name}/stream"]["frames_sha256"], name
+
+
 def test_bank_cli_udp_egress(pkg, cases, tmp_path):
     """opv-demod-bank -u PORT: stream k's frames leave as 134-byte UDP datagrams to 127.0.0.1:(PORT + k), the egress of
     `opv-modem -R` (src/opv-modem.cpp:782) for a whole bank; payloads and order equal the frame files."""
