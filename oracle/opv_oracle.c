@@ -82,8 +82,16 @@ void ora_codemod_set_pll_bandwidth(ora_codemod_t* d, double bw) { /* :561-568 */
     d->pll_beta = wn * wn / (SYMBOL_RATE * SYMBOL_RATE);
 }
 
+/* TEST HOOK (not in the reference): a perturbation of the Costas loop's initial phase, in radians.  The loop is
+ * chaotic on these signals (it never locks), so a last-bit difference in sin/cos grows until the trajectory is a
+ * different one; tests use this to measure that horizon on the oracle itself and to tell which captures have
+ * frames that are stable under it (tests/test_oracle.py::test_coherent_sensitivity). */
+static double g_codemod_perturb = 0.0;
+void ora_set_codemod_perturb(double rad) { g_codemod_perturb = rad; }
+
 size_t ora_codemod_demodulate(ora_codemod_t* d, const int16_t* iq, size_t n, double* soft_out, size_t cap) { /* :450-548 */
     size_t ns = 0;
+    d->carrier_phase += g_codemod_perturb;
     double phase_inc_f1 = TWO_PI * (-FREQ_DEV + d->freq_offset) / SAMPLE_RATE;
     double phase_inc_f2 = TWO_PI * (+FREQ_DEV + d->freq_offset) / SAMPLE_RATE;
     for (size_t sym = 0; sym < n / ORA_SPS; ++sym) {

@@ -98,6 +98,7 @@ int ora_viterbi_decode(const int32_t* soft_in2144, uint8_t* bits1072);
 int ora_frame_decode(const double* soft2144, uint8_t* out134);
 void ora_quantise(const double* soft2144, int32_t* q2144, double* scale_out); /* :856-866, no deinterleave */
 void ora_lfsr_table(uint8_t* out134);
+void ora_set_codemod_perturb(double rad); /* test hook, see opv_oracle.c */
 
 /* ---- whole chain: main() drivers (:995-1216) ---- */
 typedef struct {

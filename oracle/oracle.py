@@ -88,6 +88,7 @@ def lib():
     if _lib is None:
         build()
         L = C.CDLL(os.path.join(HERE, "libopv_oracle.so"))
+        L.ora_set_codemod_perturb.argtypes = [C.c_double]
         L.ora_estimate_offset.restype = C.c_double
         L.ora_estimate_offset.argtypes = [C.c_void_p, C.c_size_t]
         L.ora_demodulate.restype = C.c_size_t
@@ -173,8 +174,17 @@ class RunResult:
 
 
 def run(iq: np.ndarray, streaming: bool, afc_alpha: float = 0.001, init_offset: float | None = None,
-        want_soft: bool = True, coherent: bool = False, pll_bw: float = 50.0) -> RunResult:
-    """Whole chain through the C restatement (main() drivers, src/opv-demod.cpp:995-1216)."""
+        want_soft: bool = True, coherent: bool = False, pll_bw: float = 50.0, coherent_perturb: float = 0.0) -> RunResult:
+    """Whole chain through the C restatement (main() drivers, src/opv-demod.cpp:995-1216).
+    coherent_perturb: test hook, initial Costas phase offset in radians (0 = the reference's behaviour)."""
+    lib().ora_set_codemod_perturb(float(coherent_perturb))
+    try:
+        return _run(iq, streaming, afc_alpha, init_offset, want_soft, coherent, pll_bw)
+    finally:
+        lib().ora_set_codemod_perturb(0.0)
+
+
+def _run(iq, streaming, afc_alpha, init_offset, want_soft, coherent, pll_bw) -> RunResult:
     a = _iq(iq)
     n = a.size // 2
     capf = n // FRAME_SAMPLES + 4

@@ -45,6 +45,25 @@ def _soft_err(got, ref):
     return float(np.max(np.abs(got - ref)) / (np.sqrt(np.mean(ref ** 2)) + 1e-300))
 
 
+def _ref_binary_many(ora, caps, args):
+    """stdout of the UNMODIFIED reference opv-demod for many captures, one process per capture, cores in parallel."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(c):
+        return subprocess.run([ora.REF_DEMOD, *args], input=np.ascontiguousarray(c).tobytes(), capture_output=True).stdout
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        return list(ex.map(one, caps))
+
+
+def _oracle_many(ora, caps, streaming):
+    """ora.run over many captures on all host cores (the C restatement runs outside the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        return list(ex.map(lambda c: ora.run(c, streaming), caps))
+
+
 def _run_bank(pkg, caps, streaming, **kw):
     n = max(max(c.shape[0] for c in caps), 64)
     bank = pkg.DemodBank(len(caps), streaming=streaming, max_samples=n, **kw)
@@ -536,10 +555,11 @@ def test_baseline_config_shapes_at_scale(shape, pkg, ora):
     import torch
 
     if shape == "configs2_4096_cfo_delay":
-        S, n_frames, kw, picks = 4096, 3, dict(ebn0_lo_db=8.0, ebn0_hi_db=16.0, cfo_max_hz=2000.0, frac_delay=True,
-                                               max_lead=30000), [0, 1, 511, 1024, 2047, 3000, 4095]
+        S, n_frames, kw = 4096, 3, dict(ebn0_lo_db=8.0, ebn0_hi_db=16.0, cfo_max_hz=2000.0, frac_delay=True, max_lead=30000)
     else:
-        S, n_frames, kw, picks = 16384, 2, dict(ebn0_lo_db=2.0, ebn0_hi_db=10.0, max_lead=4000), [0, 777, 8191, 8192, 16383]
+        S, n_frames, kw = 16384, 2, dict(ebn0_lo_db=2.0, ebn0_hi_db=10.0, max_lead=4000)
+    # 256 randomly chosen streams (plus the corners) are checked against the oracle on the same bytes
+    picks = sorted(set([0, 1, S // 2 - 1, S // 2, S - 1]) | set(int(x) for x in np.random.default_rng(S).choice(S, 256, replace=False)))
     n = n_frames * 86720 + kw["max_lead"] + 4000
     stride = (n + 63) // 64 * 64
     buf = torch.zeros((S, stride), dtype=torch.int32, device="cuda")
@@ -555,10 +575,15 @@ def test_baseline_config_shapes_at_scale(shape, pkg, ora):
     assert c["frames_decoded"] == fr.data.shape[0] <= S * n_frames
     assert c["frames_ready"] == c["frames_decoded"] + c["frames_dropped"]
     assert c["acs"] == c["frames_decoded"] * 1072 * 64
-    for s in picks:
-        host = buf[s, :n].cpu().numpy().view(np.int16).reshape(n, 2)
-        ref = ora.run(host, True)
-        assert np.array_equal(fr.of_stream(s), ref.frames), (shape, s)
+    host = buf[torch.tensor(picks, device="cuda"), :n].cpu().numpy().view(np.int16).reshape(len(picks), n, 2)
+    refs = _oracle_many(ora, [host[k] for k in range(len(picks))], True)
+    by_stream = {}
+    order = np.argsort(fr.stream, kind="stable")
+    bounds = np.searchsorted(fr.stream[order], np.arange(S + 1))
+    for k, s in enumerate(picks):
+        ref = refs[k]
+        got = fr.data[order[bounds[s]:bounds[s + 1]]]
+        assert np.array_equal(got, ref.frames), (shape, s)
         assert _soft_err(bank.get_soft(s), ref.soft) < SOFT_TOL
         assert [(t, i, c2) for (t, i, c2, _, _) in bank.poll_events(s)] == [(t, i, c2) for (t, i, c2, _, _) in ref.events]
     bank.bert_check(sp)
@@ -602,6 +627,86 @@ def test_baseline_config3_long_captures_random_starts_and_dropouts(pkg, ora):
             lost += sum(1 for (t, _, _) in ev if t == 5)  # LOCKED -> HUNTING
         assert lost >= 8, "the long dropouts must exercise the miss limit and re-acquisition"
         bank.close()
+
+
+def test_baseline_config1_full_length_streams_vs_reference_binary(pkg, ora):
+    """BASELINE.json configs[1] at its real capture length: 64 streams x 10 s (250 frames, 21.7 M samples each) with AWGN
+    2..10 dB, each demodulated in full by the UNMODIFIED reference binary (one process per stream, host cores in
+    parallel) and by the GPU chain in time tiles; frame count and every byte of every stream must agree."""
+    import torch
+
+    if not os.path.exists(ora.REF_DEMOD):
+        pytest.skip("oracle/_ref/opv-demod not built")
+    S, n_frames = 64, 250
+    n = n_frames * 86720 + 8000
+    stride = (n + 63) // 64 * 64
+    buf = torch.zeros((S, stride), dtype=torch.int32, device="cuda")
+    sp = pkg.make_synth(S, n_frames, stride, n, seed=31, ebn0_lo_db=2.0, ebn0_hi_db=10.0, max_lead=4000)
+    pkg.synth_bank(buf.data_ptr(), sp)
+    bank = pkg.DemodBank(S, streaming=True)
+    for e in list(range(25 * 86720, n, 25 * 86720)) + [n]:      # ten time tiles, runs queued ahead
+        bank.attach_device_iq(buf.data_ptr(), stride, e, keepalive=buf)
+        bank.run(final=(e == n), sync=False)
+    fr = bank.poll_frames()
+    host = buf[:, :n].cpu().numpy().view(np.int16).reshape(S, n, 2)
+    outs = _ref_binary_many(ora, [host[k] for k in range(S)], ["-s", "-r", "-q"])
+    for s in range(S):
+        ref = np.frombuffer(outs[s], np.uint8).reshape(-1, 134)
+        got = fr.of_stream(s)
+        assert got.shape == ref.shape and np.array_equal(got, ref), (s, got.shape, ref.shape)
+    assert fr.data.shape[0] > 0.5 * S * n_frames
+    bank.close()
+
+
+def test_baseline_config3_true_length_60s_vs_reference_binary(pkg, ora):
+    """BASELINE.json configs[3] at its real length: 8 streams x 60 s (1,500 frames, 130 M samples each: sample positions
+    and symbol counts deep into the range where FP32 or 32-bit indexing would break) with random frame starts and
+    dropouts shorter and longer than the 5-miss flywheel limit (:60), whole streams against the reference binary."""
+    import torch
+
+    from tools import captures as cap
+
+    if not os.path.exists(ora.REF_DEMOD):
+        pytest.skip("oracle/_ref/opv-demod not built")
+    S, n_frames = 8, 1500
+    base = cap.clean_bert(n_frames).astype(np.float32) * np.float32(0.25)
+    rng = np.random.default_rng(60)
+    caps = []
+    for k in range(S):
+        lead = int(rng.integers(0, 86720))
+        x = rng.standard_normal((base.shape[0] + lead, 2), dtype=np.float32)
+        ebn0 = float(rng.uniform(6.0, 12.0))
+        a = cap.AMP * 0.25
+        x *= np.float32(np.sqrt(a * a * cap.SPS / (0.5 * 10.0 ** (ebn0 / 10.0)) / 2.0))
+        sig = base.copy()
+        for _ in range(12):                                     # dropouts: the signal disappears, the noise stays
+            start = int(rng.integers(3, n_frames - 10)) * 86720 + int(rng.integers(0, 86720))
+            sig[start:start + int(rng.choice([20000, 86720, 3 * 86720, 6 * 86720 + 4000]))] = 0
+        x[lead:] += sig
+        np.rint(x, out=x)
+        np.clip(x, -32768, 32767, out=x)
+        caps.append(x.astype(np.int16))
+        del sig, x
+    n = max(c.shape[0] for c in caps)
+    stride = (n + 63) // 64 * 64
+    buf = torch.zeros((S, stride), dtype=torch.int32, device="cuda")
+    for k, c in enumerate(caps):
+        buf[k, :c.shape[0]] = torch.from_numpy(np.ascontiguousarray(c).view(np.int32).reshape(-1)).cuda()
+    lens = np.array([c.shape[0] for c in caps], np.int64)
+    bank = pkg.DemodBank(S, streaming=True)
+    bank.attach_device_iq(buf.data_ptr(), stride, lens, keepalive=buf)
+    bank.run(final=True)
+    fr = bank.poll_frames()
+    outs = _ref_binary_many(ora, caps, ["-s", "-r", "-q"])
+    lost = 0
+    for s in range(S):
+        ref = np.frombuffer(outs[s], np.uint8).reshape(-1, 134)
+        got = fr.of_stream(s)
+        assert got.shape == ref.shape and np.array_equal(got, ref), (s, got.shape, ref.shape)
+        assert bank.stream_info(s)["n_samples_used"] > 129_000_000
+        lost += sum(1 for (t, _, _, _, _) in bank.poll_events(s) if t == 5)
+    assert lost >= 8
+    bank.close()
 
 
 def test_abi_error_behaviour(pkg):
