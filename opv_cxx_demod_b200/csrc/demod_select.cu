@@ -3,7 +3,8 @@
 // A stream is a strictly serial recurrence (symbol n+1's window position and LO step depend on symbol n), so the
 // parallel axes are streams and the inside of one symbol, and the fastest organisation depends on how many streams
 // there are per SM:
-//   lanes_per_stream = 32   one warp per stream (kernels_demod_warp.cu): lowest per-symbol latency, for small banks
+//   lanes_per_stream = 32   one warp per stream (kernels_demod_warp.cu): low per-symbol latency, for small banks
+//   lanes_per_stream = 64   two warps per stream (window + AFC roles, same file): the AFC chain leaves the critical path
 //   lanes_per_stream = 96   channel-bank kernel, three role warps per 32 streams (kernels_demod_bank.cu): large banks
 #include <cuda_runtime.h>
 
@@ -26,6 +27,7 @@ cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodSt
     if (n_streams <= 0) return cudaSuccess;
     const int L = lanes_per_stream > 0 ? lanes_per_stream : demod_auto_lanes(n_streams);
     if (L >= 96) return launch_demod_bank(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    if (L >= 64) return launch_demod_warp2(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     return launch_demod_warp(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
 }
 

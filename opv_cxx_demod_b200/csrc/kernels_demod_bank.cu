@@ -297,21 +297,21 @@ __device__ __forceinline__ void role_stage(BankSmem& sm, int s, int stream, cons
         const int w0 = sm.w0[s];
         req = (w0 < 0 ? 0 : w0) & ~(kChunk - 1);
     }
-    uint4 bufA[2 * NB], bufB[2 * NB];
-    int idxA = -1, idxB = -1;  // row index of the batch held in the buffer (-1: empty)
-    auto request = [&](uint4 (&buf)[2 * NB], int& idx) {
-        const int w0 = ld_vol(&sm.w0[s]);
-        const bool can = ld_vol(&sm.live[s]) != 0 && req + kBatch <= w0 + kRingRows - kChunk && req < view.rel_end;
+    uint4 buf[2 * NB];
+    int idx = -1;  // row index of the batch in flight (-1: none)
+    auto room = [&]() {
+        return ld_vol(&sm.live[s]) != 0 && req + kBatch <= ld_vol(&sm.w0[s]) + kRingRows - kChunk && req < view.rel_end;
+    };
+    auto request = [&]() {
         idx = -1;
-        if (can) {
+        if (room()) {
 #pragma unroll
             for (int c = 0; c < NB; ++c) chunk_load(view, req + kChunk * c, wide, buf[2 * c], buf[2 * c + 1]);
             idx = req;
             req += kBatch;
         }
-        return can;
     };
-    auto retire = [&](uint4 (&buf)[2 * NB], int& idx) {
+    auto retire = [&]() {  // batches are stored in request order: `fill` is one watermark per stream
         if (idx >= 0) {
 #pragma unroll
             for (int c = 0; c < NB; ++c) chunk_store<QX>(sm, s, idx + kChunk * c, buf[2 * c], buf[2 * c + 1]);
@@ -323,16 +323,18 @@ __device__ __forceinline__ void role_stage(BankSmem& sm, int s, int stream, cons
     // One pass per symbol, woken by the window warp's tick (a named barrier: a blocked warp costs no issue slots; the
     // first version polled the window position and spent ~670 instructions per symbol doing so, on a sub-partition
     // it shares with another CTA's window warp).  Steady state: the batch requested at the previous tick is stored
-    // (its loads have had a whole symbol to land), the next one is requested and stays in flight until the next tick.
-    // While the ring still has room after that (start of the launch, or a stream that consumes more than 40 samples
-    // per symbol) further batches are fetched synchronously.
-    // A tick that arrives while this warp is busy is not lost: the tick counter shows it, and the pass is repeated
-    // instead of blocking.
+    // (its loads have had a whole symbol to land) and the next one is requested and stays in flight until the next
+    // tick.  While the ring still has room after that (start of the launch, or a stream that consumes more than 40
+    // samples per symbol) further batches are fetched one after the other.  A tick that arrives while this warp is
+    // busy is not lost: the tick counter shows it, and the pass is repeated instead of blocking.
     int seen = 0;
     for (;;) {
-        retire(bufB, idxB);
-        request(bufB, idxB);
-        while (__any_sync(kFull, request(bufA, idxA))) retire(bufA, idxA);
+        retire();
+        request();
+        while (__any_sync(kFull, room())) {
+            retire();
+            request();
+        }
         if (ld_vol(&sm.exit_flag)) break;
         const int t = ld_vol(&sm.tick);
         if (t == seen) bar_sync<kBarTick, 64>();
