@@ -44,7 +44,8 @@ void upload_constants() {
     cudaMemcpyToSymbol(c_lfsr, t, sizeof(t));
 }
 
-constexpr int kDecWarps = 4;
+constexpr int kDecWarps = 2;  // 64-thread CTAs (22 KB, 4,096 registers): one fits beside four resident channel-bank CTAs, so the
+                              // decoder of time tile t runs while tile t+1 is demodulated (opvd_api.cu, back stream)
 constexpr int kDecWords = kFrameBits / 16;                 // 67 decision words per lane
 constexpr int kDecBytesPerWarp = kDecWords * 32 * 4;       // 8576 B, aliased as 1072 doubles for the scale sum
 constexpr int kQBytesPerWarp = kEncodedBits;               // deinterleaved 3-bit symbols, one byte each
@@ -256,7 +257,7 @@ static int decode_grid(int n_tasks) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int per_sm = 5;  // 5 CTAs x 4 warps x 10.9 KB = 217 KB of shared memory per SM
+    const int per_sm = 10;  // 10 CTAs x 2 warps x 10.9 KB = 217 KB of shared memory per SM
     int want = (n_tasks + kDecWarps - 1) / kDecWarps;
     int cap = sms * per_sm;
     return want < cap ? (want > 0 ? want : 1) : cap;

@@ -13,7 +13,7 @@
 
 namespace opvd {
 
-constexpr int kTrackWarps = 4;
+constexpr int kTrackWarps = 2;  // small CTAs: they fit beside resident demodulator CTAs (overlap with the next tile)
 
 __global__ void __launch_bounds__(32 * kTrackWarps)
 track_kernel(SoftBuffers so, TrackState* __restrict__ tstate, int n_streams,
