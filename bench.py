@@ -507,12 +507,31 @@ def main():
         e_s = time.perf_counter() - t0
         e_s = reduce_max_ms(e_s, dev)
         e_val = S * world * n_e * args.steps / e_s / 1e6
+        # the platform's host-to-device ceiling with all ranks copying at once (plain pinned cudaMemcpyAsync of the same
+        # buffer, no kernels): what the e2e rate is a fraction of
+        dst = torch.empty((S, n_e), dtype=torch.int32, device=dev)
+        dst.copy_(host, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        reps_c = 3
+        for _ in range(reps_c):
+            dst.copy_(host, non_blocking=True)
+        barrier()
+        c_s = reduce_max_ms(time.perf_counter() - t0, dev)
+        h2d_ceiling = S * n_e * 4 * reps_c * world / c_s / 1e9
+        del dst
         e2e = {"value": round(e_val, 2), "unit": UNIT, "h2d_bytes_per_step": int(S * n_e * 4), "d2h_bytes_per_step": d2h,
                "sample": f"{S} streams x {nf_e} frames ({n_e} samples) per rank per step from pinned host memory, "
                          f"pushed and run in {tiles} time tiles through a {2 * tile_max + FRAME_SAMPLES + 256}-sample device ring "
                          f"per stream; the rate is bound by the host-to-device copies ({S * n_e * 4 * args.steps / e_s / 1e9:.1f} GB/s "
                          f"per GPU), so it does not depend on the capture length",
-               "frames_per_step": int(fr.data.shape[0])}
+               "frames_per_step": int(fr.data.shape[0]),
+               "h2d_gbs": round(S * world * n_e * 4 * args.steps / e_s / 1e9, 2),
+               "h2d_ceiling_gbs": round(h2d_ceiling, 2),
+               "frac_of_h2d_ceiling": round(S * world * n_e * 4 * args.steps / e_s / 1e9 / h2d_ceiling, 4),
+               "h2d_ceiling_note": "all ranks copying the same pinned buffers at once with plain cudaMemcpyAsync, no kernels; "
+                                   "on this box every GPU hangs off NUMA node 0, so the ceiling itself does not scale "
+                                   "linearly with the rank count"}
         ebank.close()
         del host
 
