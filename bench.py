@@ -320,7 +320,7 @@ def run_sustained(args, pkg, torch, np, dev, local_rank, S, bank_buf, barrier, r
     host = torch.empty((S, FRAME_SAMPLES), dtype=torch.int32, pin_memory=True)
     host.copy_(bank_buf[:, MAX_LEAD + FRAME_SAMPLES: MAX_LEAD + 2 * FRAME_SAMPLES])
     torch.cuda.synchronize()
-    sbank = pkg.DemodBank(S, streaming=True, device=local_rank, max_samples=3 * FRAME_SAMPLES, max_frames=8,
+    sbank = pkg.DemodBank(S, streaming=True, device=local_rank, max_samples=3 * FRAME_SAMPLES + 512, max_frames=8,
                           lanes_per_stream=args.lanes)
     frames = []
     d2h = 0

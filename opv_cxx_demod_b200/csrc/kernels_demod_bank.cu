@@ -9,7 +9,7 @@
 //   AFC     phase detector, AFC loop, LO steps z (handed back first: the next symbol's Horner needs nothing else),
 //           then the LO powers z^10, z^20, zeta^40 for the gate combination (:289-310)
 //   STAGE   HBM -> transposed shared-memory ring, one batch of 32-byte sectors per lane in flight, 2-4 symbols
-//           ahead of the window; woken once per symbol by the window warp
+//           ahead of the window; paces itself with __nanosleep (about one round per symbol)
 // The AFC chain of symbol n overlaps the early/late + timing part of symbol n.  Hardware placement (tools/warp_place.cu):
 // warp w of the j-th resident 3-warp CTA sits on SM sub-partition (3 j + w) & 3, so with four resident CTAs every
 // sub-partition hosts exactly one warp of each role.
@@ -40,7 +40,7 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kQBias = 0x80000000u;
 
 // named barriers (0 is __syncthreads)
-enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3, kBarTick = 4 };
+enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3 };
 enum : int { kFlagTone1 = 1, kFlagFirst = 2, kFlagLive = 4, kFlagExit = 8 };
 
 struct __align__(16) BankSmem {
@@ -53,8 +53,6 @@ struct __align__(16) BankSmem {
     int fill[kSpc];               // STAGE -> WINDOW: samples [.., fill) of the stream's row are in the ring
     int live[kSpc];               // WINDOW -> STAGE: stream still has symbols to demodulate in this launch
     int exit_flag;                // WINDOW -> STAGE
-    int tick;                     // WINDOW -> STAGE: symbols started so far (the wake-up barrier's payload)
-    int stage_done;               // STAGE -> WINDOW: the staging warp has left its loop
 };
 
 template <int ID, int N>
@@ -297,50 +295,38 @@ __device__ __forceinline__ void role_stage(BankSmem& sm, int s, int stream, cons
         const int w0 = sm.w0[s];
         req = (w0 < 0 ? 0 : w0) & ~(kChunk - 1);
     }
+    int pub = req;  // samples [.., pub) are in the ring and published in sm.fill (stored in request order: one watermark)
     uint4 buf[2 * NB];
-    int idx = -1;  // row index of the batch in flight (-1: none)
-    auto room = [&]() {
-        return ld_vol(&sm.live[s]) != 0 && req + kBatch <= ld_vol(&sm.w0[s]) + kRingRows - kChunk && req < view.rel_end;
-    };
-    auto request = [&]() {
-        idx = -1;
-        if (room()) {
+    int idx = -1;   // row index of the batch in flight (-1: none)
+    // No blocking primitive here: the warp paces itself with __nanosleep.  (A named-barrier wake-up was tried: a blocked
+    // warp costs nothing, but one ordering slip between the watermark and the barrier deadlocks the CTA, and a hung
+    // kernel on a shared box costs more than the ~25 polling instructions per symbol this loop spends.  The first version
+    // polled every 200 ns with a heavy loop body and spent ~670 instructions per symbol, on a sub-partition it shares
+    // with another CTA's window warp.)  Steady state per round: store the batch requested before the last sleep (its
+    // loads have had ~0.7 us to land), request the next one, sleep.  A stream that is close to starving (start of a
+    // launch, end of a row, catching up after a stall) is served without sleeping.
+    for (;;) {
+        const int w0 = ld_vol(&sm.w0[s]);
+        const bool lv = ld_vol(&sm.live[s]) != 0;
+        if (idx >= 0) {
+#pragma unroll
+            for (int c = 0; c < NB; ++c) chunk_store<QX>(sm, s, idx + kChunk * c, buf[2 * c], buf[2 * c + 1]);
+            __threadfence_block();
+            pub = idx + kBatch;
+            st_vol(&sm.fill[s], pub);
+            idx = -1;
+        }
+        if (lv && req + kBatch <= w0 + kRingRows - kChunk && req < view.rel_end) {
 #pragma unroll
             for (int c = 0; c < NB; ++c) chunk_load(view, req + kChunk * c, wide, buf[2 * c], buf[2 * c + 1]);
             idx = req;
             req += kBatch;
         }
-    };
-    auto retire = [&]() {  // batches are stored in request order: `fill` is one watermark per stream
-        if (idx >= 0) {
-#pragma unroll
-            for (int c = 0; c < NB; ++c) chunk_store<QX>(sm, s, idx + kChunk * c, buf[2 * c], buf[2 * c + 1]);
-            __threadfence_block();
-            st_vol(&sm.fill[s], idx + kBatch);
-            idx = -1;
-        }
-    };
-    // One pass per symbol, woken by the window warp's tick (a named barrier: a blocked warp costs no issue slots; the
-    // first version polled the window position and spent ~670 instructions per symbol doing so, on a sub-partition
-    // it shares with another CTA's window warp).  Steady state: the batch requested at the previous tick is stored
-    // (its loads have had a whole symbol to land) and the next one is requested and stays in flight until the next
-    // tick.  While the ring still has room after that (start of the launch, or a stream that consumes more than 40
-    // samples per symbol) further batches are fetched one after the other.  A tick that arrives while this warp is
-    // busy is not lost: the tick counter shows it, and the pass is repeated instead of blocking.
-    int seen = 0;
-    for (;;) {
-        retire();
-        request();
-        while (__any_sync(kFull, room())) {
-            retire();
-            request();
-        }
+        const bool urgent = idx >= 0 && pub < w0 + kWin + 2 * kBatch;  // the window may need this batch before the next round
+        if (__any_sync(kFull, urgent)) continue;
         if (ld_vol(&sm.exit_flag)) break;
-        const int t = ld_vol(&sm.tick);
-        if (t == seen) bar_sync<kBarTick, 64>();
-        seen = t;
+        __nanosleep(700);
     }
-    st_vol(&sm.stage_done, 1);
     __syncthreads();  // (2)
 }
 
@@ -367,10 +353,9 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     c.init(st, sb, so, stream, valid, mode, final_flag);
     sm.w0[s] = c.w0;
     sm.live[s] = c.live ? 1 : 0;
-    if (s == 0) { sm.exit_flag = 0; sm.tick = 0; sm.stage_done = 0; }
+    if (s == 0) sm.exit_flag = 0;
     __syncthreads();  // (1) symbol 0 published
     bool any_live = __any_sync(kFull, c.live);
-    int tick = 0;
     while (any_live) {
         const bool first = c.sym_in_call == 0;
         bar_sync<kBarZ, 64>();
@@ -402,18 +387,10 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
             else st_vol(&sm.live[s], 0);
         }
         any_live = __any_sync(kFull, c.live);
-        if (any_live) {  // wake the staging warp: the window has moved on
-            st_vol(&sm.tick, ++tick);
-            bar_arrive<kBarTick, 64>();
-        }
     }
     sm.flags[s] = kFlagExit;
     st_vol(&sm.exit_flag, 1);
     bar_arrive<kBarO, 64>();
-    while (!ld_vol(&sm.stage_done)) {  // keep ticking until the staging warp has seen the exit flag
-        bar_arrive<kBarTick, 64>();
-        __nanosleep(100);
-    }
     if (valid) c.persist(st, so, dstate, stream, counters);
     __syncthreads();  // (2)
 }

@@ -1,22 +1,26 @@
 #!/bin/bash
-# Round 2, call E: bank kernel with in-order barrier-woken staging; two-warp-per-stream kernel; tests; bench; ncu.
+# Round 2, call E: bank kernel with sleep-paced in-order staging; two-warp-per-stream kernel; tests; bench; ncu.
+# Every step has a tight timeout and the script stops at the first hang.
 set -x
 mkdir -p gpurun_out
-P="timeout 90 python tools/probe.py --streams 18944 --frames 6 --reps 2"
+timeout 60 python tools/probe.py --streams 4096 --frames 3 --reps 1 --lanes 96 2>&1 | tail -1 | cut -c1-200 || exit 1
+timeout 60 python tools/probe.py --streams 1024 --frames 6 --reps 1 --lanes 64 2>&1 | tail -1 | cut -c1-200 || exit 1
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "one_bank or ring or granularity or clock_offset" 2>&1 | tail -5
+P="timeout 60 python tools/probe.py --streams 18944 --frames 6 --reps 2"
 for QX in 1 2 0; do
-  OPVD_BANK_QX=$QX $P --lanes 96 2>&1 | tail -1 | cut -c1-200
+  OPVD_BANK_QX=$QX $P --lanes 96 2>&1 | tail -1 | cut -c1-200 || exit 1
 done
 for S in 4096 8192 37888; do
-  timeout 90 python tools/probe.py --streams $S --frames 6 --reps 2 --lanes 96 2>&1 | tail -1 | cut -c1-200
+  timeout 60 python tools/probe.py --streams $S --frames 6 --reps 2 --lanes 96 2>&1 | tail -1 | cut -c1-200
 done
 for L in 32 64; do
-  timeout 90 python tools/probe.py --streams 1024 --frames 25 --reps 2 --lanes $L 2>&1 | tail -1 | cut -c1-200
+  timeout 60 python tools/probe.py --streams 1024 --frames 25 --reps 2 --lanes $L 2>&1 | tail -1 | cut -c1-200
 done
-timeout 90 python tools/probe.py --streams 2048 --frames 12 --reps 2 --lanes 64 2>&1 | tail -1 | cut -c1-200
-timeout 90 python tools/probe.py --streams 2048 --frames 12 --reps 2 --lanes 96 2>&1 | tail -1 | cut -c1-200
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r02_e.json 2> gpurun_out/bench_r02_e.err
+timeout 60 python tools/probe.py --streams 2048 --frames 12 --reps 2 --lanes 64 2>&1 | tail -1 | cut -c1-200
+timeout 60 python tools/probe.py --streams 2048 --frames 12 --reps 2 --lanes 96 2>&1 | tail -1 | cut -c1-200
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+timeout 420 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r02_e.json 2> gpurun_out/bench_r02_e.err
 tail -c 3500 gpurun_out/bench_r02_e.json; tail -5 gpurun_out/bench_r02_e.err
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:demod_bank -c 1 -f -o gpurun_out/prof_bank_r02_e \
+timeout 240 ncu --set full --clock-control none --import-source on -k regex:demod_bank -c 1 -f -o gpurun_out/prof_bank_r02_e \
     python tools/probe.py --streams 18944 --frames 2 --reps 1 --lanes 96 > gpurun_out/ncu_bank_r02_e.log 2>&1
 tail -2 gpurun_out/ncu_bank_r02_e.log
