@@ -55,7 +55,10 @@ def parse_args():
     ap.add_argument("--bank-streams", type=int, default=0,
                     help="streams per GPU of the channel-bank leg (0 = 4 CTAs x 32 streams per SM, 18,944 on a B200)")
     ap.add_argument("--bank-frames", type=int, default=14, help="frames per stream of the channel-bank legs")
-    ap.add_argument("--bank-tiles", type=int, default=7, help="time tiles per step of the channel-bank legs")
+    ap.add_argument("--bank-tiles", type=int, default=1,
+                    help="time tiles per step of the channel-bank legs (1: the whole resident bank in one run; with more, the tracker "
+                         "and the decoder of tile t share the SMs with the demodulator of tile t+1, which costs the demodulator "
+                         "more than the overlap saves on this kernel: measured 73.0 ms with 7 tiles against 67.3 ms with 1)")
     ap.add_argument("--strong-streams", type=int, default=16384, help="total streams of the strong-scaling bank")
     ap.add_argument("--sustained-tiles", type=int, default=30, help="one-frame tiles pushed from pinned host memory in the sustained leg")
     ap.add_argument("--no-bank", action="store_true", help="skip the channel-bank legs")
@@ -462,7 +465,9 @@ def main():
                             "peak_dfma_per_s": mb["dfma_per_s"],
                             "frac": round(counters["samples"] * fp64_ops_per_sample / (demod_ms * 1e-3) / mb["dfma_per_s"], 4)}
     dec_s = max(per_kernel["decode"] / args.steps * 1e-3, 1e-9)
-    viterbi = {"acs_per_s": round(counters["acs"] / dec_s, 1), "decode_ms": round(per_kernel["decode"] / args.steps, 3)}
+    viterbi = {"acs_per_s": round(counters["acs"] / dec_s, 1), "decode_ms": round(per_kernel["decode"] / args.steps, 3),
+               "note": "decode_ms is the elapsed time of the decoder launches; with several time tiles per step they share the "
+                       "SMs with the demodulator of the next tile, so the clean ACS rate is the channel_bank leg's (one tile)"}
     if mb:
         # 15 warp-instructions per trellis step of 64 states (2 per lane) = 7.5 integer lane-operations per ACS
         viterbi["int_ops_per_acs"] = 7.5
@@ -594,6 +599,12 @@ def main():
         del sbuf
         torch.cuda.empty_cache()
 
+    if channel_bank and mb:  # the Viterbi kernel alone (the bank leg runs the chain without overlap)
+        cb = channel_bank
+        acs_s = cb["frames_per_s"] * 68608.0 * cb["ms_per_step"] / max(cb["kernel_ms_per_step"]["decode"], 1e-9) if cb["tiles_per_step"] == 1 else None
+        if acs_s:
+            viterbi.update({"acs_per_s_alone": round(acs_s, 1), "frac_of_int32_peak_alone": round(acs_s * 7.5 / mb["alu_ops_per_s"], 4),
+                            "frac_of_dpx_peak_alone": round(acs_s / 2.0 / mb["dpx_vibmin_add_per_s"], 4)})
     if rank == 0:
         n_launch = (4 * len(ends) + 1) * args.steps  # est + demod + track + decode (+ log advance) per tile
         line = {

@@ -40,7 +40,7 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kQBias = 0x80000000u;
 
 // named barriers (0 is __syncthreads)
-enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3 };
+enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3, kBarWin = 4, kBarEl = 5 };
 enum : int { kFlagTone1 = 1, kFlagFirst = 2, kFlagLive = 4, kFlagExit = 8 };
 
 struct __align__(16) BankSmem {
@@ -48,6 +48,7 @@ struct __align__(16) BankSmem {
     double o[4][kSpc];            // WINDOW -> AFC: O1.r, O1.i, O2.r, O2.i
     double z[4][kSpc];            // AFC -> WINDOW: z1.r, z1.i, z2.r, z2.i
     double pw[10][kSpc];          // AFC -> WINDOW: q1, q2, qq1, qq2, zeta40
+    double el[12][kSpc];          // AFC -> WINDOW (ELB variant): H0 (F1), H0 (F2), H5 (F1), H5 (F2), s0, s60
     int flags[kSpc];              // WINDOW -> AFC: kFlag*
     int w0[kSpc];                 // WINDOW -> STAGE: row-relative sample index of window slot 0 of the current symbol
     int fill[kSpc];               // STAGE -> WINDOW: samples [.., fill) of the stream's row are in the ring
@@ -228,7 +229,9 @@ __device__ __forceinline__ void load_pow(const BankSmem& sm, int s, BankPow& pw)
 
 // ---------------------------------------------------------------------------------------------------------------
 // AFC role.  NW = threads taking part in the z / power hand-offs (64: one window warp, 96: two).
-template <int NW>
+// ELB: this warp also evaluates the early / late block sums H0, H5 of both tones (bank_el_blocks) while the window warp
+// works on the on-time blocks; it is woken by kBarWin when the window of the symbol has been published.
+template <int NW, int QX, bool ELB>
 __device__ __forceinline__ void role_afc(BankSmem& sm, int s, int stream, bool valid, DemodState* dstate, double afc_alpha) {
     const DemodState* d0 = dstate + stream;
     BankAfc afc = {d0->freq_offset, d0->ph1, d0->ph2, d0->p1, d0->p2};
@@ -254,6 +257,20 @@ __device__ __forceinline__ void role_afc(BankSmem& sm, int s, int stream, bool v
     publish_z();
     publish_pow();
     for (;;) {
+        if (ELB) {
+            bar_sync<kBarWin, 64>();  // the window of this symbol is published (or the launch is over)
+            if (ld_vol(&sm.exit_flag)) break;
+            const int w0 = ld_vol(&sm.w0[s]);
+            wait_window(sm, s, ld_vol(&sm.live[s]) != 0, w0);
+            const uint32_t* const win = &sm.ring[w0 & (kRingRows - 1)][s];
+            auto slot = [&](int k, double& I, double& Q) { unpack_ring<QX>(win[k * kSpc], k, I, Q); };
+            BankElBlocks e;
+            bank_el_blocks(slot, lo.z1, lo.z2, e);
+            sm.el[0][s] = e.H0a.r; sm.el[1][s] = e.H0a.i; sm.el[2][s] = e.H0b.r; sm.el[3][s] = e.H0b.i;
+            sm.el[4][s] = e.H5a.r; sm.el[5][s] = e.H5a.i; sm.el[6][s] = e.H5b.r; sm.el[7][s] = e.H5b.i;
+            sm.el[8][s] = e.s0.r; sm.el[9][s] = e.s0.i; sm.el[10][s] = e.s60.r; sm.el[11][s] = e.s60.i;
+            bar_arrive<kBarEl, 64>();
+        }
         bar_sync<kBarO, 64>();
         const int fl = sm.flags[s];
         if (fl & kFlagExit) break;  // warp-uniform: the window warp sets it on every lane
@@ -334,7 +351,7 @@ __device__ __forceinline__ void role_stage(BankSmem& sm, int s, int stream, cons
 
 // =================================================================================================================
 // Three-warp kernel: WINDOW, AFC, STAGE (96 threads)
-template <int QX>
+template <int QX, bool ELB>
 __global__ void __launch_bounds__(96, 4)
 demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
                   int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
@@ -345,7 +362,7 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     const bool valid = stream_raw < n_streams;
     const int stream = valid ? stream_raw : n_streams - 1;
 
-    if (role == 1) { role_afc<64>(sm, s, stream, valid, dstate, afc_alpha); return; }
+    if (role == 1) { role_afc<64, QX, ELB>(sm, s, stream, valid, dstate, afc_alpha); return; }
     if (role == 2) { role_stage<QX, 5>(sm, s, stream, sb, dstate); return; }
 
     DemodState st = dstate[stream];  // local memory: only the scheduler touches it
@@ -358,6 +375,7 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     bool any_live = __any_sync(kFull, c.live);
     while (any_live) {
         const bool first = c.sym_in_call == 0;
+        if (ELB) bar_arrive<kBarWin, 64>();  // the AFC warp may start on the early / late blocks of this window
         bar_sync<kBarZ, 64>();
         BankLo lo;
         load_lo(sm, s, lo);
@@ -379,7 +397,15 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         cplx fixE = {0.0, 0.0};
         if (first && c.live) fixE = first_fix_cold<QX>(win, c.f, tone1 ? lo.z1 : lo.z2);  // :237, once per call
         double eE, eL;
-        bank_early_late(slot, c.f, tone1, lo, pw, on, fixE, eE, eL);
+        if (ELB) {
+            bar_sync<kBarEl, 64>();  // block sums H0, H5 of both tones from the AFC warp
+            const int t = tone1 ? 0 : 2;
+            const cplx H0 = {sm.el[t][s], sm.el[t + 1][s]}, H5 = {sm.el[4 + t][s], sm.el[5 + t][s]};
+            const cplx s0 = {sm.el[8][s], sm.el[9][s]}, s60 = {sm.el[10][s], sm.el[11][s]};
+            bank_early_late_from_blocks(c.f, tone1, lo, pw, on, H0, H5, s0, s60, fixE, eE, eL);
+        } else {
+            bank_early_late(slot, c.f, tone1, lo, pw, on, fixE, eE, eL);
+        }
         if (c.live) {
             bank_timing(eE, eL, c.timing_freq, c.pos, g_fm);
             c.advance(st, mode, final_flag);
@@ -390,19 +416,20 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     }
     sm.flags[s] = kFlagExit;
     st_vol(&sm.exit_flag, 1);
-    bar_arrive<kBarO, 64>();
+    if (ELB) bar_arrive<kBarWin, 64>();  // the AFC warp waits for the next window
+    else bar_arrive<kBarO, 64>();        // ... or for the next on-time correlations
     if (valid) c.persist(st, so, dstate, stream, counters);
     __syncthreads();  // (2)
 }
 
-template <int QX>
+template <int QX, bool ELB>
 static cudaError_t launch_bank_t(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams, int mode,
                                  int final_flag, double afc_alpha, unsigned long long* counters, cudaStream_t st) {
     const size_t smem = sizeof(BankSmem);
-    cudaError_t e = cudaFuncSetAttribute(demod_bank_kernel<QX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(demod_bank_kernel<QX, ELB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (n_streams + kSpc - 1) / kSpc;
-    demod_bank_kernel<QX><<<grid, 96, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
+    demod_bank_kernel<QX, ELB><<<grid, 96, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
     return cudaGetLastError();
 }
 static int env_int(const char* name, int dflt) {
@@ -410,14 +437,18 @@ static int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-// OPVD_BANK_QX: development switch (conversion split); results are identical
+// OPVD_BANK_QX / OPVD_BANK_ELB: development switches (conversion split; early/late block sums on the AFC warp);
+// results are identical
 cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                               cudaStream_t st) {
-    static const int qx = env_int("OPVD_BANK_QX", 1);
-    if (qx == 0) return launch_bank_t<0>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
-    if (qx == 2) return launch_bank_t<2>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
-    return launch_bank_t<1>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    static const int qx = env_int("OPVD_BANK_QX", 1), elb = env_int("OPVD_BANK_ELB", 1);
+#define OPVD_BANK_CASE(Q, E) \
+    if (qx == Q && elb == E) return launch_bank_t<Q, E != 0>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st)
+    OPVD_BANK_CASE(0, 0); OPVD_BANK_CASE(1, 0); OPVD_BANK_CASE(2, 0);
+    OPVD_BANK_CASE(0, 1); OPVD_BANK_CASE(2, 1);
+#undef OPVD_BANK_CASE
+    return launch_bank_t<1, true>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
 }
 
 }  // namespace opvd

@@ -279,10 +279,20 @@ struct __align__(16) Warp2Smem {
     double zr[4][32];      // AFC -> WINDOW: z.r, z.i, R.r, R.i of every lane
     double xo[2][2];       // WINDOW -> AFC: interpolated on-time gate of F1 / F2 (carrying z^10)
     int flags;             // WINDOW -> AFC: bit 0 first symbol of a call, bit 1 exit
+    int seq_x, seq_lo;     // hand-off sequence numbers (symbols handed over so far)
 };
-enum : int { kBarX = 1, kBarLO = 2 };
-__device__ __forceinline__ void bar2_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void bar2_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+// Hand-offs are sequence numbers in shared memory that the consumer spins on: a named barrier costs ~250 cycles per
+// hand-off here (measured: the barrier version of this kernel was slower than one warp per stream), a spinning read
+// ~40, and on an SM that hosts seven streams the issue slots of a spinning warp are free.
+__device__ __forceinline__ void handoff_post(int* seq, int n, int lane) {
+    __threadfence_block();  // the payload written by this warp's lanes ...
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile int*>(seq) = n;  // ... before its sequence number
+}
+__device__ __forceinline__ void handoff_wait(const int* seq, int n) {
+    while (*reinterpret_cast<const volatile int*>(seq) != n) {}
+    __threadfence_block();
+}
 
 }  // namespace
 
@@ -293,6 +303,7 @@ demod_warp2_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     const int stream = blockIdx.x;
     DemodState st = dstate[stream];
+    if (threadIdx.x == 0) { sm.seq_x = 0; sm.seq_lo = 0; }
     __syncthreads();  // both warps have read the record before either writes it
 
     if (role == 1) {
@@ -307,11 +318,11 @@ demod_warp2_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
         double freq_offset = st.freq_offset;
         double ph_own = wl.tone ? st.ph2 : st.ph1;
         const int tone_base = lane & 16;
-        for (;;) {
+        for (int n = 1;; ++n) {
             sm.zr[0][lane] = wl.z.r; sm.zr[1][lane] = wl.z.i; sm.zr[2][lane] = wl.R.r; sm.zr[3][lane] = wl.R.i;
-            bar2_arrive(kBarLO);
-            bar2_sync(kBarX);
-            const int fl = sm.flags;
+            handoff_post(&sm.seq_lo, n, lane);
+            handoff_wait(&sm.seq_x, n);
+            const int fl = *reinterpret_cast<const volatile int*>(&sm.flags);
             if (fl & 2) break;
             const bool first = (fl & 1) != 0;
             const cplx X1 = {sm.xo[0][0], sm.xo[0][1]}, X2 = {sm.xo[1][0], sm.xo[1][1]};
@@ -366,9 +377,11 @@ demod_warp2_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
     c.issued_s = -1;
 
     // one symbol; FIRST as in WarpCtx::symbol
+    int n_hand = 0;  // symbols handed over so far
     auto symbol2 = [&](int b, uint32_t (&s5)[5], bool first) {
         const double f = c.pos - (double)b;
-        bar2_sync(kBarLO);  // LO step and slot rotation of this symbol
+        ++n_hand;
+        handoff_wait(&sm.seq_lo, n_hand);  // LO step and slot rotation of this symbol
         c.wl.z = {sm.zr[0][lane], sm.zr[1][lane]};
         c.wl.R = {sm.zr[2][lane], sm.zr[3][lane]};
         const LanePartial lp = warp_lane_partial(c.wl, s5);
@@ -386,8 +399,8 @@ demod_warp2_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
             if (c.wl.p == kWarpGateLaneE) { X.r -= fix.r; X.i -= fix.i; }
         }
         if (c.wl.p == kWarpGateLaneO) { sm.xo[c.wl.tone][0] = X.r; sm.xo[c.wl.tone][1] = X.i; }
-        if (lane == 0) sm.flags = first ? 1 : 0;
-        bar2_arrive(kBarX);  // the AFC warp takes it from here
+        if (lane == 0) *reinterpret_cast<volatile int*>(&sm.flags) = first ? 1 : 0;
+        handoff_post(&sm.seq_x, n_hand, lane);  // the AFC warp takes it from here
         const double nrm = cnorm(X);
         const double e1 = __shfl_sync(kFull, nrm, kWarpGateLaneO), e2 = __shfl_sync(kFull, nrm, 16 + kWarpGateLaneO);
         const double eE1 = __shfl_sync(kFull, nrm, kWarpGateLaneE), eL1 = __shfl_sync(kFull, nrm, kWarpGateLaneL);
@@ -427,9 +440,8 @@ demod_warp2_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
         }
         st.sym_in_call = 2;
     }
-    if (lane == 0) sm.flags = 2;
-    bar2_sync(kBarLO);   // the AFC warp's pending hand-over
-    bar2_arrive(kBarX);  // ... and its exit
+    if (lane == 0) *reinterpret_cast<volatile int*>(&sm.flags) = 2;
+    handoff_post(&sm.seq_x, n_hand + 1, lane);  // the AFC warp is waiting for symbol n_hand + 1: it gets the exit flag
     if (lane == 0) {
         DemodState* d = dstate + stream;
         d->pos = c.pos; d->timing_freq = c.timing_freq; d->origin = st.origin; d->call_len = st.call_len;
@@ -447,6 +459,7 @@ demod_warp2_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ ds
 cudaError_t launch_demod_warp2(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                                int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                                cudaStream_t st) {
+    cudaFuncSetAttribute(demod_warp2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     demod_warp2_kernel<<<n_streams, 64, 0, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
     return cudaGetLastError();
 }
@@ -454,6 +467,11 @@ cudaError_t launch_demod_warp2(const StreamBuffers& sb, const SoftBuffers& so, D
 cudaError_t launch_demod_warp(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                               cudaStream_t st) {
+    // Ask for the largest shared-memory carveout although this kernel needs 2.3 KB per CTA: the L1/shared split of an
+    // SM only changes while the SM is empty, and with a small carveout the tracker/decoder CTAs of the previous time
+    // tile (22 KB each, second CUDA stream) could not be placed beside the resident demodulator CTAs: they ran after
+    // them instead of with them.  The kernel streams its samples through cp.async.cg (L2 only), so it loses nothing.
+    cudaFuncSetAttribute(demod_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     demod_warp_kernel<<<n_streams, 32, 0, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
     return cudaGetLastError();
 }

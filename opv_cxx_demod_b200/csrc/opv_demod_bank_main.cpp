@@ -142,13 +142,17 @@ bool gather(const Options& o, Shard& sh, std::vector<Source>& src, int timeout_m
         for (size_t i = 0; i < pf.size(); ++i) {
             Source& s = src[(size_t)who[i]];
             if (!(pf[i].revents & (POLLIN | POLLHUP | POLLERR))) continue;
-            const size_t have = s.stage.size(), room = (size_t)(o.tile * 4) - have;
-            s.stage.resize(have + room);
-            const ssize_t n = s.is_udp ? recv(s.fd, s.stage.data() + have, room, MSG_DONTWAIT) : read(s.fd, s.stage.data() + have, room);
-            s.stage.resize(have + (n > 0 ? (size_t)n : 0));
-            if (n > 0) { s.seen_data = true; got_any = true; }
-            else if (n == 0 && !s.is_udp && (!s.is_fifo || s.seen_data)) s.eof = true;  // a FIFO nobody has opened yet reads 0
-            else if (n < 0 && errno != EAGAIN && errno != EWOULDBLOCK && errno != EINTR) s.eof = true;
+            for (;;) {  // drain the descriptor: a socket hands out one datagram per recv
+                const size_t have = s.stage.size(), room = (size_t)(o.tile * 4) - have;
+                if (room < (s.is_udp ? 65536u : 1u)) break;
+                s.stage.resize(have + room);
+                const ssize_t n = s.is_udp ? recv(s.fd, s.stage.data() + have, room, MSG_DONTWAIT) : read(s.fd, s.stage.data() + have, room);
+                s.stage.resize(have + (n > 0 ? (size_t)n : 0));
+                if (n > 0) { s.seen_data = true; got_any = true; continue; }
+                if (n == 0 && !s.is_udp && (!s.is_fifo || s.seen_data)) s.eof = true;  // a FIFO nobody has opened yet reads 0
+                else if (n < 0 && errno != EAGAIN && errno != EWOULDBLOCK && errno != EINTR) s.eof = true;
+                break;
+            }
         }
     }
     if (got_any) idle_s = 0.0;

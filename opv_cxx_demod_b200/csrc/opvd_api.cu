@@ -101,6 +101,7 @@ struct opvd_handle {
     std::vector<int32_t> polled_events;
 
     bool final_seen = false;
+    bool est_all_done = false;  // every stream's offset estimate has been decided by an enqueued run: no more est launches
 };
 
 namespace {
@@ -261,6 +262,7 @@ int opvd_create(const opvd_config* cfg, opvd_handle** out) {
                                                             have_init, cfg->init_offset_hz);
     h->h_avail.assign(h->S, 0);
     h->polled_events.assign(h->S, 0);
+    h->est_all_done = have_init != 0;  // -o: the estimate is skipped altogether (:1031)
     if (cfg->max_samples > 0) {
         h->stride = (cfg->max_samples + 63) & ~63ll;
         h->ring = cfg->mode == OPVD_MODE_STREAM;
@@ -328,6 +330,7 @@ int opvd_reset(opvd_handle* h) {
     for (double& a : h->acc_ms) a = 0.0;
     h->have_first = h->have_times = false;
     h->final_seen = false;
+    h->est_all_done = h->cfg.mode == OPVD_MODE_STREAM && h->cfg.have_init_offset;
     CK(cudaStreamSynchronize(h->st));
     CK(cudaGetLastError());
     return OPVD_OK;
@@ -479,7 +482,15 @@ int opvd_run(opvd_handle* h, int final_flag) {
         h->have_first = true;
     }
     CK(cudaEventRecord(h->ev_t[slot][0], h->st));
-    launch_estimate(sb, h->d_dstate, h->d_est, h->S, h->cfg.mode, final_flag ? 1 : 0, h->st);
+    if (!h->est_all_done) {
+        launch_estimate(sb, h->d_dstate, h->d_est, h->S, h->cfg.mode, final_flag ? 1 : 0, h->st);
+        // the estimate of a stream is decided by the first run that sees a full chunk of it (stream mode, :1030-1038)
+        // or by the final run (batch mode :1166; short streams are never estimated): once that holds for every stream
+        // the kernel has nothing left to do
+        int64_t min_avail = INT64_MAX;
+        for (int s = 0; s < h->S; ++s) min_avail = std::min(min_avail, h->h_avail[s]);
+        h->est_all_done = final_flag || (h->cfg.mode == OPVD_MODE_STREAM && min_avail >= kChunkSamples);
+    }
     CK(cudaEventRecord(h->ev_t[slot][1], h->st));
     if (h->cfg.coherent && h->cfg.mode == OPVD_MODE_BATCH) {
         // -p <hz> verbatim like the reference (set_pll_bandwidth, :1149; -p 0 freezes the loop); NaN = default 50 (:946)
