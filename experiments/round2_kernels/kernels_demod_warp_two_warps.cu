@@ -264,6 +264,206 @@ demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     }
 }
 
+// =================================================================================================================
+// Two warps per stream (lanes_per_stream 64): the same arithmetic with the per-symbol chain cut in two.  In the
+// one-warp kernel a symbol is one serial chain of ~1,240 cycles (profiles/): partial sums and gates 460, timing loop
+// 215, ring upkeep 210, AFC chain + LO steps 360, and nothing but the AFC chain needs the on-time correlations.  Here
+//   warp 0 (WINDOW)  partial sums, gates, soft symbol, timing loop, ring upkeep, next window
+//   warp 1 (AFC)     phase detector, AFC loop, previous correlations, LO step z and slot rotations R of all 32 lanes
+// run concurrently: warp 0 hands over the two on-time gate values (32 bytes) as soon as they exist and needs z, R
+// back only when the next symbol's partial sums start, after its own timing loop and ring upkeep.
+namespace {
+
+struct __align__(16) Warp2Smem {
+    uint32_t ring[kRingWords];
+    double zr[4][32];      // AFC -> WINDOW: z.r, z.i, R.r, R.i of every lane
+    double xo[2][2];       // WINDOW -> AFC: interpolated on-time gate of F1 / F2 (carrying z^10)
+    int flags;             // WINDOW -> AFC: bit 0 first symbol of a call, bit 1 exit
+    int seq_x, seq_lo;     // hand-off sequence numbers (symbols handed over so far)
+};
+// Hand-offs are sequence numbers in shared memory that the consumer spins on: a named barrier costs ~250 cycles per
+// hand-off here (measured: the barrier version of this kernel was slower than one warp per stream), a spinning read
+// ~40, and on an SM that hosts seven streams the issue slots of a spinning warp are free.
+__device__ __forceinline__ void handoff_post(int* seq, int n, int lane) {
+    __threadfence_block();  // the payload written by this warp's lanes ...
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile int*>(seq) = n;  // ... before its sequence number
+}
+__device__ __forceinline__ void handoff_wait(const int* seq, int n) {
+    while (*reinterpret_cast<const volatile int*>(seq) != n) {}
+    __threadfence_block();
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(64)
+demod_warp2_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
+                   int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
+    __shared__ Warp2Smem sm;
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const int stream = blockIdx.x;
+    DemodState st = dstate[stream];
+    if (threadIdx.x == 0) { sm.seq_x = 0; sm.seq_lo = 0; }
+    __syncthreads();  // both warps have read the record before either writes it
+
+    if (role == 1) {
+        // ============================================================================================= AFC warp
+        const FastMathTable K = load_table_pinned();
+        WarpLane wl;
+        warp_lane_init(wl, lane, K);
+        warp_lane_lo(wl, st.freq_offset);  // general version: a -o offset may exceed the fast range
+        wl.prev = wl.tone ? st.p2 : st.p1;
+        bool prev_zero = wl.prev.r == 0.0 && wl.prev.i == 0.0;
+        cplx RP = cmul(wl.R, wl.prev);
+        double freq_offset = st.freq_offset;
+        double ph_own = wl.tone ? st.ph2 : st.ph1;
+        const int tone_base = lane & 16;
+        for (int n = 1;; ++n) {
+            sm.zr[0][lane] = wl.z.r; sm.zr[1][lane] = wl.z.i; sm.zr[2][lane] = wl.R.r; sm.zr[3][lane] = wl.R.i;
+            handoff_post(&sm.seq_lo, n, lane);
+            handoff_wait(&sm.seq_x, n);
+            const int fl = *reinterpret_cast<const volatile int*>(&sm.flags);
+            if (fl & 2) break;
+            const bool first = (fl & 1) != 0;
+            const cplx X1 = {sm.xo[0][0], sm.xo[0][1]}, X2 = {sm.xo[1][0], sm.xo[1][1]};
+            const cplx X = wl.tone ? X2 : X1;              // what the on-time gate lane of this tone holds
+            const bool tone1 = cnorm(X1) > cnorm(X2);      // :272, :291 (same bits as the window warp's decision)
+            const bool x_zero = cnorm(X) == 0.0;
+            double pd_own = 0.0;
+            if (!first) pd_own = warp_lane_afc_phase(wl, X, RP, x_zero || prev_zero, ph_own, K);
+            const cplx z50 = shfl_c(wl.R, tone_base | 10);   // R of lane p = 10 is z^50 = z^10 * z^40
+            wl.prev = cmul(X, cconj(z50));                    // :309-310
+            prev_zero = x_zero;
+            ph_own = warp_wrap_phase(fma(40.0, wl.inc, ph_own), K);  // :250-262
+            if (!first) {
+                const double pd = __shfl_sync(kFull, pd_own, tone1 ? kWarpGateLaneO : 16 + kWarpGateLaneO);
+                warp_afc_loop(freq_offset, pd, afc_alpha, K);
+                warp_lane_lo_fast(wl, freq_offset, K);
+            }
+            RP = cmul(wl.R, wl.prev);
+        }
+        __syncthreads();  // the window warp has written the record
+        const double ph1 = __shfl_sync(kFull, ph_own, 0), ph2 = __shfl_sync(kFull, ph_own, 16);
+        const cplx p1 = shfl_c(wl.prev, kWarpGateLaneO), p2 = shfl_c(wl.prev, 16 + kWarpGateLaneO);
+        if (lane == 0) {
+            DemodState* d = dstate + stream;
+            d->freq_offset = freq_offset; d->ph1 = ph1; d->ph2 = ph2; d->p1 = p1; d->p2 = p2;
+        }
+        return;
+    }
+
+    // ================================================================================================= WINDOW warp
+    WarpCtx c;
+    c.K = load_table_pinned();
+    c.lane = lane;
+    c.ring = sm.ring;
+    c.ring_s = smem_u32(sm.ring);
+    const long long avail = sb.avail[stream];
+    const RowView view = make_row_view(sb, stream, st.origin);
+    c.set_view(view);
+    const long long row0 = view.base_abs;
+    c.avail_rel = (int)(avail - row0);
+    c.soft_row = so.soft + (long long)stream * so.stride;
+    c.soft_wrap = so.ring ? (int)so.stride : 0x7fffffff;
+    c.soft_idx = (int)soft_pos(so, st.n_sym);
+    c.n_new = 0;
+    c.afc_alpha = afc_alpha;
+    warp_lane_init(c.wl, lane, c.K);
+    c.lane_slot = 5 * (c.wl.p > 12 ? 12 : c.wl.p);
+    c.tone_base = lane & 16;
+    c.pos = st.pos;
+    c.timing_freq = st.timing_freq;
+    c.ph_own = 0.0;
+    c.issued_s = -1;
+
+    // one symbol; FIRST as in WarpCtx::symbol
+    int n_hand = 0;  // symbols handed over so far
+    auto symbol2 = [&](int b, uint32_t (&s5)[5], bool first) {
+        const double f = c.pos - (double)b;
+        ++n_hand;
+        handoff_wait(&sm.seq_lo, n_hand);  // LO step and slot rotation of this symbol
+        c.wl.z = {sm.zr[0][lane], sm.zr[1][lane]};
+        c.wl.R = {sm.zr[2][lane], sm.zr[3][lane]};
+        const LanePartial lp = warp_lane_partial(c.wl, s5);
+        const cplx Fh = shfl_down_c(lp.F, 8);
+        cplx acc = lp.W;
+#pragma unroll
+        for (int d = 1; d <= 4; d <<= 1) {
+            const cplx o = shfl_down_c(acc, d);
+            acc = {acc.r + o.r, acc.i + o.i};
+        }
+        cplx X = warp_lane_gate(c.wl, f, acc, Fh, lp.F);
+        if (first) {
+            const uint32_t* win = c.ring + ((c.origin_rel + b - kWinLead) & kRingMask);
+            const cplx fix = first_symbol_fix_w([&](int k) { return win[k]; }, f, c.wl.z);
+            if (c.wl.p == kWarpGateLaneE) { X.r -= fix.r; X.i -= fix.i; }
+        }
+        if (c.wl.p == kWarpGateLaneO) { sm.xo[c.wl.tone][0] = X.r; sm.xo[c.wl.tone][1] = X.i; }
+        if (lane == 0) *reinterpret_cast<volatile int*>(&sm.flags) = first ? 1 : 0;
+        handoff_post(&sm.seq_x, n_hand, lane);  // the AFC warp takes it from here
+        const double nrm = cnorm(X);
+        const double e1 = __shfl_sync(kFull, nrm, kWarpGateLaneO), e2 = __shfl_sync(kFull, nrm, 16 + kWarpGateLaneO);
+        const double eE1 = __shfl_sync(kFull, nrm, kWarpGateLaneE), eL1 = __shfl_sync(kFull, nrm, kWarpGateLaneL);
+        const double eE2 = __shfl_sync(kFull, nrm, 16 + kWarpGateLaneE), eL2 = __shfl_sync(kFull, nrm, 16 + kWarpGateLaneL);
+        bool tone1;
+        const double soft = warp_uniform_timing(e1, e2, eE1, eL1, eE2, eL2, c.timing_freq, c.pos, tone1, c.K);
+        if (lane == 0) c.soft_row[c.soft_idx] = soft;
+        if (++c.soft_idx == c.soft_wrap) c.soft_idx = 0;
+        ++c.n_new;
+        const int b_next = __double2int_rz(c.pos);  // pos >= 0: truncation == floor (:125)
+        c.load_window(b_next, s5);
+        return b_next;
+    };
+
+    const long long n_sym0 = st.n_sym, origin0 = st.origin;
+    for (;;) {
+        st.n_sym = n_sym0 + c.n_new;
+        if (!demod_schedule(st, c.pos, mode, avail, final_flag != 0)) break;
+        c.origin_rel = (int)(st.origin - row0);
+        asm volatile("" : "+r"(c.origin_rel));
+        const int call_len_i = (int)st.call_len;
+        const double call_len_d = (double)st.call_len;
+        int b = __double2int_rz(c.pos);
+        uint32_t s5[5];
+        if (c.issued_s < 0) c.ring_prime(c.origin_rel + b - kWinLead);
+        else c.ring_maintain(c.origin_rel + b - kWinLead);
+        c.load_window(b, s5);
+        if (st.sym_in_call == 0) {
+            b = symbol2(b, s5, true);
+            st.sym_in_call = 1;
+            if (!((c.pos + 40.0) + 10.0 < call_len_d)) continue;
+        }
+        for (;;) {
+            if (b + 52 >= call_len_i && !((c.pos + 40.0) + 10.0 < call_len_d)) break;
+            c.ring_maintain(c.origin_rel + b - kWinLead);
+            b = symbol2(b, s5, false);
+        }
+        st.sym_in_call = 2;
+    }
+    if (lane == 0) *reinterpret_cast<volatile int*>(&sm.flags) = 2;
+    handoff_post(&sm.seq_x, n_hand + 1, lane);  // the AFC warp is waiting for symbol n_hand + 1: it gets the exit flag
+    if (lane == 0) {
+        DemodState* d = dstate + stream;
+        d->pos = c.pos; d->timing_freq = c.timing_freq; d->origin = st.origin; d->call_len = st.call_len;
+        d->n_sym = st.n_sym; d->sym_in_call = st.sym_in_call; d->flags = st.flags;
+        so.n_sym[stream] = st.n_sym;
+        unsigned long long dsym = (unsigned long long)(st.n_sym - n_sym0);
+        unsigned long long dsmp = (unsigned long long)(st.origin - origin0);
+        if (st.flags & kFlagDone) dsmp = (unsigned long long)(avail - origin0);
+        if (dsym) atomicAdd(&counters[kCtrSymbols], dsym);
+        if (dsmp) atomicAdd(&counters[kCtrSamples], dsmp);
+    }
+    __syncthreads();
+}
+
+cudaError_t launch_demod_warp2(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
+                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
+                               cudaStream_t st) {
+    cudaFuncSetAttribute(demod_warp2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    demod_warp2_kernel<<<n_streams, 64, 0, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_demod_warp(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                               cudaStream_t st) {

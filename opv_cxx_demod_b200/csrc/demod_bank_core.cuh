@@ -122,6 +122,40 @@ OPVD_HD void bank_on_blocks(Win win, cplx z1, cplx z2, cplx (&A)[4], cplx (&B)[4
     }
 }
 
+// The same sums in two passes of two blocks (8 chains instead of 16) with the samples of step j-1 fetched and converted
+// before the Horner products of step j are written down: fewer live accumulators, deeper conversion prefetch.  Same
+// values (a block sum does not depend on what is interleaved with it).
+template <class Win>
+OPVD_HD void bank_on_blocks_2x2(Win win, cplx z1, cplx z2, cplx (&A)[4], cplx (&B)[4], cplx& s10, cplx& s20, cplx& s40) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        double I0, Q0, I1, Q1;
+        win(10 * (2 * h + 1) + 9, I0, Q0);
+        win(10 * (2 * h + 2) + 9, I1, Q1);
+        A[2 * h] = {I0, Q0}; B[2 * h] = {I0, Q0};
+        A[2 * h + 1] = {I1, Q1}; B[2 * h + 1] = {I1, Q1};
+        win(10 * (2 * h + 1) + 8, I0, Q0);
+        win(10 * (2 * h + 2) + 8, I1, Q1);
+#pragma unroll
+        for (int j = 8; j >= 0; --j) {
+            double nI0 = 0.0, nQ0 = 0.0, nI1 = 0.0, nQ1 = 0.0;
+            if (j > 0) {
+                win(10 * (2 * h + 1) + j - 1, nI0, nQ0);
+                win(10 * (2 * h + 2) + j - 1, nI1, nQ1);
+            }
+            hstep(A[2 * h], z1, I0, Q0);
+            hstep(B[2 * h], z2, I0, Q0);
+            hstep(A[2 * h + 1], z1, I1, Q1);
+            hstep(B[2 * h + 1], z2, I1, Q1);
+            if (j == 0) {
+                if (h == 0) { s10 = {I0, Q0}; s20 = {I1, Q1}; }
+                else s40 = {I1, Q1};
+            }
+            I0 = nI0; Q0 = nQ0; I1 = nI1; Q1 = nQ1;
+        }
+    }
+}
+
 // interpolated gate from the raw gate sum X and its shifted-window edge term dX = s[last+1]*z^40 - s[first]:
 //   sum_k y[k] z^k = g*X + h*dX,   g = (1-f) + f*conj(z),  h = f*conj(z)     (demod_core.cuh)
 OPVD_HD cplx bank_interp(cplx g, cplx h, cplx X, cplx last, cplx first, cplx z40) {

@@ -4,7 +4,6 @@
 // parallel axes are streams and the inside of one symbol, and the fastest organisation depends on how many streams
 // there are per SM:
 //   lanes_per_stream = 32   one warp per stream (kernels_demod_warp.cu): low per-symbol latency, for small banks
-//   lanes_per_stream = 64   two warps per stream (window + AFC roles, same file): the AFC chain leaves the critical path
 //   lanes_per_stream = 96   channel-bank kernel, three role warps per 32 streams (kernels_demod_bank.cu): large banks
 #include <cuda_runtime.h>
 
@@ -13,11 +12,11 @@
 namespace opvd {
 
 int demod_auto_lanes(int n_streams) {
-    // Measured crossover between the warp-per-stream kernel and the bank kernel: ~16 streams per SM
-    // (profiles/README.md).
+    // Measured crossover (profiles/gpu_r02_f.log): the bank kernel needs 2.38 ms per frame for anything up to one CTA
+    // per SM (4,736 streams); the warp-per-stream kernel 1.41 ms per frame at 1,024 streams and 2.59 ms at 1,280.
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if ((long long)n_streams <= 16ll * sms) return 32;
+    if ((long long)n_streams <= 8ll * sms) return 32;
     return 96;
 }
 
@@ -27,7 +26,6 @@ cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodSt
     if (n_streams <= 0) return cudaSuccess;
     const int L = lanes_per_stream > 0 ? lanes_per_stream : demod_auto_lanes(n_streams);
     if (L >= 96) return launch_demod_bank(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
-    if (L >= 64) return launch_demod_warp2(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
     return launch_demod_warp(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
 }
 

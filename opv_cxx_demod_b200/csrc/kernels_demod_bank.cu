@@ -351,7 +351,9 @@ __device__ __forceinline__ void role_stage(BankSmem& sm, int s, int stream, cons
 
 // =================================================================================================================
 // Three-warp kernel: WINDOW, AFC, STAGE (96 threads)
-template <int QX, bool ELB>
+// ELB: the AFC warp evaluates the early / late block sums (measured: no gain, the AFC warp's chain becomes the critical
+// path and it takes issue slots from another CTA's window warp).  OB2: on-time blocks in two passes of two.
+template <int QX, bool ELB, bool OB2>
 __global__ void __launch_bounds__(96, 4)
 demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
                   int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
@@ -383,7 +385,8 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         const uint32_t* const win = &sm.ring[c.w0 & (kRingRows - 1)][s];
         auto slot = [&](int k, double& I, double& Q) { unpack_ring<QX>(win[k * kSpc], k, I, Q); };
         cplx A[4], B[4], s10, s20, s40;
-        bank_on_blocks(slot, lo.z1, lo.z2, A, B, s10, s20, s40);
+        if (OB2) bank_on_blocks_2x2(slot, lo.z1, lo.z2, A, B, s10, s20, s40);
+        else bank_on_blocks(slot, lo.z1, lo.z2, A, B, s10, s20, s40);
         bar_sync<kBarPow, 64>();
         BankPow pw;
         load_pow(sm, s, pw);
@@ -422,14 +425,14 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     __syncthreads();  // (2)
 }
 
-template <int QX, bool ELB>
+template <int QX, bool ELB, bool OB2>
 static cudaError_t launch_bank_t(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams, int mode,
                                  int final_flag, double afc_alpha, unsigned long long* counters, cudaStream_t st) {
     const size_t smem = sizeof(BankSmem);
-    cudaError_t e = cudaFuncSetAttribute(demod_bank_kernel<QX, ELB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(demod_bank_kernel<QX, ELB, OB2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (n_streams + kSpc - 1) / kSpc;
-    demod_bank_kernel<QX, ELB><<<grid, 96, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
+    demod_bank_kernel<QX, ELB, OB2><<<grid, 96, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
     return cudaGetLastError();
 }
 static int env_int(const char* name, int dflt) {
@@ -437,18 +440,19 @@ static int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-// OPVD_BANK_QX / OPVD_BANK_ELB: development switches (conversion split; early/late block sums on the AFC warp);
-// results are identical
+// OPVD_BANK_QX / _ELB / _OB2: development switches (conversion split; early/late block sums on the AFC warp; on-time
+// blocks in two passes); results are identical
 cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                               cudaStream_t st) {
-    static const int qx = env_int("OPVD_BANK_QX", 1), elb = env_int("OPVD_BANK_ELB", 1);
-#define OPVD_BANK_CASE(Q, E) \
-    if (qx == Q && elb == E) return launch_bank_t<Q, E != 0>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st)
-    OPVD_BANK_CASE(0, 0); OPVD_BANK_CASE(1, 0); OPVD_BANK_CASE(2, 0);
-    OPVD_BANK_CASE(0, 1); OPVD_BANK_CASE(2, 1);
+    static const int qx = env_int("OPVD_BANK_QX", 1), elb = env_int("OPVD_BANK_ELB", 0), ob2 = env_int("OPVD_BANK_OB2", 0);
+#define OPVD_BANK_CASE(Q, E, O) \
+    if (qx == Q && elb == E && ob2 == O)  \
+        return launch_bank_t<Q, E != 0, O != 0>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st)
+    OPVD_BANK_CASE(0, 0, 0); OPVD_BANK_CASE(2, 0, 0); OPVD_BANK_CASE(1, 1, 0);
+    OPVD_BANK_CASE(0, 0, 1); OPVD_BANK_CASE(1, 0, 1); OPVD_BANK_CASE(2, 0, 1);
 #undef OPVD_BANK_CASE
-    return launch_bank_t<1, true>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    return launch_bank_t<1, false, false>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
 }
 
 }  // namespace opvd

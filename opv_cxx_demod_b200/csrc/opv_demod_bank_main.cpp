@@ -155,7 +155,9 @@ bool gather(const Options& o, Shard& sh, std::vector<Source>& src, int timeout_m
             }
         }
     }
-    if (got_any) idle_s = 0.0;
+    bool any_seen = false;  // the idle clock starts with the first byte: a bank that is waiting for its senders is not idle
+    for (int k = 0; k < sh.count; ++k) any_seen = any_seen || src[(size_t)(sh.first + k)].seen_data;
+    if (got_any || !any_seen) idle_s = 0.0;
     else idle_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() + 1e-4;
     if (o.idle_exit >= 0.0 && idle_s >= o.idle_exit) {  // UDP inputs have no EOF: stop after a quiet period
         for (int k = 0; k < sh.count; ++k) src[(size_t)(sh.first + k)].eof = true;

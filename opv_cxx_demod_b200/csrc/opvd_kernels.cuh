@@ -120,11 +120,6 @@ cudaError_t launch_demod_warp(const StreamBuffers& sb, const SoftBuffers& so, De
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                               cudaStream_t st);
 
-// two warps per stream (window + AFC), kernels_demod_warp.cu; lanes_per_stream == 64
-cudaError_t launch_demod_warp2(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
-                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
-                               cudaStream_t st);
-
 // channel-bank variant (kernels_demod_bank.cu): 32 streams per 96-thread CTA, three free-running role warps;
 // selected by launch_demod for lanes_per_stream == 96
 cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,

@@ -65,9 +65,9 @@ def test_bank_cli_no_cpu_fallback_and_help(built, tmp_path):
 
     assert os.path.exists(built.BANK_CLI_PATH)
     p = subprocess.run([built.BANK_CLI_PATH, "-h"], capture_output=True)
-    assert p.returncode == 0 and b"FILE" in p.stderr and b"-s" in p.stderr
+    assert p.returncode == 0 and b"INPUT" in p.stderr and b"-s" in p.stderr and b"--devices" in p.stderr
     p = subprocess.run([built.BANK_CLI_PATH], capture_output=True)
-    assert p.returncode == 2 and b"no input files" in p.stderr
+    assert p.returncode == 2 and b"no inputs" in p.stderr
     if torch.cuda.is_available():
         return
     f = tmp_path / "a.iq"
