@@ -444,7 +444,7 @@ typedef struct {
 
 static void feed_soft(run_ctx_t* c, const double* soft, size_t n) { /* :1045-1065 == :1186-1205 */
     ora_result_t* r = c->res;
-    static double payload[ORA_ENCODED_BITS];
+    double payload[ORA_ENCODED_BITS]; /* on the stack: the tests run many captures on parallel threads */
     for (size_t i = 0; i < n; ++i) {
         ora_event_t ev[2]; int n_ev = 0; double q;
         int ready = ora_tracker_process(&c->tracker, soft[i], c->total_symbols + i, payload, &q, ev, &n_ev);

@@ -577,7 +577,6 @@ def test_baseline_config_shapes_at_scale(shape, pkg, ora):
     assert c["acs"] == c["frames_decoded"] * 1072 * 64
     host = buf[torch.tensor(picks, device="cuda"), :n].cpu().numpy().view(np.int16).reshape(len(picks), n, 2)
     refs = _oracle_many(ora, [host[k] for k in range(len(picks))], True)
-    by_stream = {}
     order = np.argsort(fr.stream, kind="stable")
     bounds = np.searchsorted(fr.stream[order], np.arange(S + 1))
     for k, s in enumerate(picks):

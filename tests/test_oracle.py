@@ -136,3 +136,21 @@ def test_coherent_mode_is_chaotic_in_the_last_bit(cases, ora):
     # and the hook itself is inert at zero
     iq = cases["awgn8"]
     assert np.array_equal(ora.run(iq, False, coherent=True).soft, ora.run(iq, False, coherent=True, coherent_perturb=0.0).soft)
+
+
+def test_oracle_is_reentrant(ora):
+    """The parity tests run the oracle over hundreds of captures on a thread pool (the C code runs outside the GIL):
+    results must not depend on what the other threads are doing (no static scratch buffers).  Random payloads: with
+    the BERT captures every thread decodes the same frames and a shared buffer goes unnoticed."""
+    from concurrent.futures import ThreadPoolExecutor
+    from tools import captures as cap
+
+    caps = [cap.clean_random(6, seed)[0] for seed in range(8)]
+    serial = [ora.run(c, True) for c in caps]
+    assert all(r.frames.shape[0] == 6 for r in serial)
+    jobs = list(range(8)) * 12
+    with ThreadPoolExecutor(max_workers=16) as ex:
+        got = list(ex.map(lambda k: ora.run(caps[k], True), jobs))
+    for k, r in zip(jobs, got):
+        assert np.array_equal(r.frames, serial[k].frames) and np.array_equal(r.soft, serial[k].soft), k
+        assert r.events == serial[k].events
