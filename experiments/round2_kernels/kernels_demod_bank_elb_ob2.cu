@@ -32,24 +32,23 @@ namespace opvd {
 namespace {
 
 constexpr int kSpc = 32;             // streams per CTA
-constexpr int kMirrorRows = 64;      // rows 0..63 of the ring repeated behind its last row
+constexpr int kRingRows = 256;       // samples per stream resident in shared memory (power of two)
+constexpr int kMirrorRows = 64;      // rows 0..63 repeated after row 255
+constexpr int kRows = kRingRows + kMirrorRows;
 constexpr int kChunk = 8;            // samples per 32-byte sector
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kQBias = 0x80000000u;
 
 // named barriers (0 is __syncthreads)
-enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3 };
+enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3, kBarWin = 4, kBarEl = 5 };
 enum : int { kFlagTone1 = 1, kFlagFirst = 2, kFlagLive = 4, kFlagExit = 8 };
 
-// RING = samples per stream resident in shared memory (a multiple of 8).  The ring is what limits the number of
-// resident CTAs per SM: 256 rows -> 45.0 KB -> 4 CTAs, 240 -> 5, 176 -> 6, 144 -> 7.
-template <int RING>
 struct __align__(16) BankSmem {
-    static constexpr int kRingRows = RING;
-    uint32_t ring[RING + kMirrorRows][kSpc];
+    uint32_t ring[kRows][kSpc];   // 40 KB
     double o[4][kSpc];            // WINDOW -> AFC: O1.r, O1.i, O2.r, O2.i
     double z[4][kSpc];            // AFC -> WINDOW: z1.r, z1.i, z2.r, z2.i
     double pw[10][kSpc];          // AFC -> WINDOW: q1, q2, qq1, qq2, zeta40
+    double el[12][kSpc];          // AFC -> WINDOW (ELB variant): H0 (F1), H0 (F2), H5 (F1), H5 (F2), s0, s60
     int flags[kSpc];              // WINDOW -> AFC: kFlag*
     int w0[kSpc];                 // WINDOW -> STAGE: row-relative sample index of window slot 0 of the current symbol
     int fill[kSpc];               // STAGE -> WINDOW: samples [.., fill) of the stream's row are in the ring
@@ -113,16 +112,9 @@ __device__ __forceinline__ void chunk_load(const RowView& v, int rel, bool wide,
         b = make_uint4(0u, 0u, 0u, 0u);
     }
 }
-// ring row of row-relative sample index idx (idx >= -RING: the first window of a stream starts kWinLead samples early)
-template <int RING>
-__device__ __forceinline__ int ring_row(int idx) {
-    if ((RING & (RING - 1)) == 0) return idx & (RING - 1);
-    return (int)((unsigned)(idx + RING) % (unsigned)RING);
-}
-template <int QX, class SM>
-__device__ __forceinline__ void chunk_store(SM& sm, int s, int idx, uint4 a, uint4 b) {
-    constexpr int kRingRows = SM::kRingRows;
-    const int r = ring_row<kRingRows>(idx);
+template <int QX>
+__device__ __forceinline__ void chunk_store(BankSmem& sm, int s, int idx, uint4 a, uint4 b) {
+    const int r = idx & (kRingRows - 1);
     const uint32_t w[8] = {ring_word<QX>(a.x), ring_word<QX>(a.y), ring_word<QX>(a.z), ring_word<QX>(a.w),
                            ring_word<QX>(b.x), ring_word<QX>(b.y), ring_word<QX>(b.z), ring_word<QX>(b.w)};
 #pragma unroll
@@ -217,20 +209,17 @@ struct WindowCtl {
     }
 };
 
-template <class SM>
-__device__ __forceinline__ void wait_window(SM& sm, int s, bool live, int w0) {
+__device__ __forceinline__ void wait_window(BankSmem& sm, int s, bool live, int w0) {
     // normally true at once: the staging warp runs 2-4 symbols ahead
     while (!__all_sync(kFull, !live || ld_vol(&sm.fill[s]) >= w0 + kWin)) {}
     __threadfence_block();
 }
-template <class SM>
-__device__ __forceinline__ void load_lo(const SM& sm, int s, BankLo& lo) {
+__device__ __forceinline__ void load_lo(const BankSmem& sm, int s, BankLo& lo) {
     lo.z1 = {sm.z[0][s], sm.z[1][s]};
     lo.z2 = {sm.z[2][s], sm.z[3][s]};
     lo.inc1 = 0.0; lo.inc2 = 0.0;
 }
-template <class SM>
-__device__ __forceinline__ void load_pow(const SM& sm, int s, BankPow& pw) {
+__device__ __forceinline__ void load_pow(const BankSmem& sm, int s, BankPow& pw) {
     pw.q1 = {sm.pw[0][s], sm.pw[1][s]};
     pw.q2 = {sm.pw[2][s], sm.pw[3][s]};
     pw.qq1 = {sm.pw[4][s], sm.pw[5][s]};
@@ -240,8 +229,10 @@ __device__ __forceinline__ void load_pow(const SM& sm, int s, BankPow& pw) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // AFC role.  NW = threads taking part in the z / power hand-offs (64: one window warp, 96: two).
-template <int NW, class SM>
-__device__ __forceinline__ void role_afc(SM& sm, int s, int stream, bool valid, DemodState* dstate, double afc_alpha) {
+// ELB: this warp also evaluates the early / late block sums H0, H5 of both tones (bank_el_blocks) while the window warp
+// works on the on-time blocks; it is woken by kBarWin when the window of the symbol has been published.
+template <int NW, int QX, bool ELB>
+__device__ __forceinline__ void role_afc(BankSmem& sm, int s, int stream, bool valid, DemodState* dstate, double afc_alpha) {
     const DemodState* d0 = dstate + stream;
     BankAfc afc = {d0->freq_offset, d0->ph1, d0->ph2, d0->p1, d0->p2};
     BankLo lo;
@@ -266,6 +257,20 @@ __device__ __forceinline__ void role_afc(SM& sm, int s, int stream, bool valid, 
     publish_z();
     publish_pow();
     for (;;) {
+        if (ELB) {
+            bar_sync<kBarWin, 64>();  // the window of this symbol is published (or the launch is over)
+            if (ld_vol(&sm.exit_flag)) break;
+            const int w0 = ld_vol(&sm.w0[s]);
+            wait_window(sm, s, ld_vol(&sm.live[s]) != 0, w0);
+            const uint32_t* const win = &sm.ring[w0 & (kRingRows - 1)][s];
+            auto slot = [&](int k, double& I, double& Q) { unpack_ring<QX>(win[k * kSpc], k, I, Q); };
+            BankElBlocks e;
+            bank_el_blocks(slot, lo.z1, lo.z2, e);
+            sm.el[0][s] = e.H0a.r; sm.el[1][s] = e.H0a.i; sm.el[2][s] = e.H0b.r; sm.el[3][s] = e.H0b.i;
+            sm.el[4][s] = e.H5a.r; sm.el[5][s] = e.H5a.i; sm.el[6][s] = e.H5b.r; sm.el[7][s] = e.H5b.i;
+            sm.el[8][s] = e.s0.r; sm.el[9][s] = e.s0.i; sm.el[10][s] = e.s60.r; sm.el[11][s] = e.s60.i;
+            bar_arrive<kBarEl, 64>();
+        }
         bar_sync<kBarO, 64>();
         const int fl = sm.flags[s];
         if (fl & kFlagExit) break;  // warp-uniform: the window warp sets it on every lane
@@ -295,12 +300,9 @@ __device__ __forceinline__ void role_afc(SM& sm, int s, int stream, bool valid, 
 
 // ---------------------------------------------------------------------------------------------------------------
 // STAGE role.  NB chunks (32-byte sectors) per batch and lane, two batches in flight.
-template <int QX, int NB, class SM>
-__device__ __forceinline__ void role_stage(SM& sm, int s, int stream, const StreamBuffers& sb, const DemodState* dstate) {
+template <int QX, int NB>
+__device__ __forceinline__ void role_stage(BankSmem& sm, int s, int stream, const StreamBuffers& sb, const DemodState* dstate) {
     constexpr int kBatch = kChunk * NB;
-    constexpr int kRingRows = SM::kRingRows;
-    // a batch in flight is urgent when the window could need it before the next round (about half a symbol later)
-    constexpr int kUrgent = kRingRows >= 240 ? kWin + 2 * kBatch : kWin + 40 + kChunk;
     const RowView view = make_row_view(sb, stream, dstate[stream].origin);  // same base as the window warp
     const bool wide = ((reinterpret_cast<uintptr_t>(sb.iq) | (uintptr_t)(sb.stride * 4)) & 31u) == 0;
     sm.fill[s] = -(1 << 30);
@@ -337,7 +339,7 @@ __device__ __forceinline__ void role_stage(SM& sm, int s, int stream, const Stre
             idx = req;
             req += kBatch;
         }
-        const bool urgent = idx >= 0 && pub < w0 + kUrgent;  // the window may need this batch before the next round
+        const bool urgent = idx >= 0 && pub < w0 + kWin + 2 * kBatch;  // the window may need this batch before the next round
         if (__any_sync(kFull, urgent)) continue;
         if (ld_vol(&sm.exit_flag)) break;
         __nanosleep(700);
@@ -349,22 +351,21 @@ __device__ __forceinline__ void role_stage(SM& sm, int s, int stream, const Stre
 
 // =================================================================================================================
 // Three-warp kernel: WINDOW, AFC, STAGE (96 threads)
-// RING / MINB: ring rows per stream and the resident CTAs per SM they allow.  The register cap is written out
-// (65,536 / (96 MINB) rounded down to the allocation unit of 8): __launch_bounds__' own choice is more conservative.
-template <int QX, int RING, int MINB>
-__global__ void __maxnreg__(MINB == 4 ? 168 : MINB == 5 ? 136 : MINB == 6 ? 112 : 96)
+// ELB: the AFC warp evaluates the early / late block sums (measured: no gain, the AFC warp's chain becomes the critical
+// path and it takes issue slots from another CTA's window warp).  OB2: on-time blocks in two passes of two.
+template <int QX, bool ELB, bool OB2>
+__global__ void __launch_bounds__(96, 4)
 demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
                   int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using SM = BankSmem<RING>;
-    SM& sm = *reinterpret_cast<SM*>(smem_raw);
+    BankSmem& sm = *reinterpret_cast<BankSmem*>(smem_raw);
     const int s = threadIdx.x & 31, role = threadIdx.x >> 5;
     const int stream_raw = blockIdx.x * kSpc + s;
     const bool valid = stream_raw < n_streams;
     const int stream = valid ? stream_raw : n_streams - 1;
 
-    if (role == 1) { role_afc<64>(sm, s, stream, valid, dstate, afc_alpha); return; }
-    if (role == 2) { role_stage<QX, (RING >= 176 ? 5 : 3)>(sm, s, stream, sb, dstate); return; }
+    if (role == 1) { role_afc<64, QX, ELB>(sm, s, stream, valid, dstate, afc_alpha); return; }
+    if (role == 2) { role_stage<QX, 5>(sm, s, stream, sb, dstate); return; }
 
     DemodState st = dstate[stream];  // local memory: only the scheduler touches it
     WindowCtl c;
@@ -376,14 +377,16 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     bool any_live = __any_sync(kFull, c.live);
     while (any_live) {
         const bool first = c.sym_in_call == 0;
+        if (ELB) bar_arrive<kBarWin, 64>();  // the AFC warp may start on the early / late blocks of this window
         bar_sync<kBarZ, 64>();
         BankLo lo;
         load_lo(sm, s, lo);
         wait_window(sm, s, c.live, c.w0);
-        const uint32_t* const win = &sm.ring[ring_row<RING>(c.w0)][s];
+        const uint32_t* const win = &sm.ring[c.w0 & (kRingRows - 1)][s];
         auto slot = [&](int k, double& I, double& Q) { unpack_ring<QX>(win[k * kSpc], k, I, Q); };
         cplx A[4], B[4], s10, s20, s40;
-        bank_on_blocks(slot, lo.z1, lo.z2, A, B, s10, s20, s40);
+        if (OB2) bank_on_blocks_2x2(slot, lo.z1, lo.z2, A, B, s10, s20, s40);
+        else bank_on_blocks(slot, lo.z1, lo.z2, A, B, s10, s20, s40);
         bar_sync<kBarPow, 64>();
         BankPow pw;
         load_pow(sm, s, pw);
@@ -397,7 +400,15 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         cplx fixE = {0.0, 0.0};
         if (first && c.live) fixE = first_fix_cold<QX>(win, c.f, tone1 ? lo.z1 : lo.z2);  // :237, once per call
         double eE, eL;
-        bank_early_late(slot, c.f, tone1, lo, pw, on, fixE, eE, eL);
+        if (ELB) {
+            bar_sync<kBarEl, 64>();  // block sums H0, H5 of both tones from the AFC warp
+            const int t = tone1 ? 0 : 2;
+            const cplx H0 = {sm.el[t][s], sm.el[t + 1][s]}, H5 = {sm.el[4 + t][s], sm.el[5 + t][s]};
+            const cplx s0 = {sm.el[8][s], sm.el[9][s]}, s60 = {sm.el[10][s], sm.el[11][s]};
+            bank_early_late_from_blocks(c.f, tone1, lo, pw, on, H0, H5, s0, s60, fixE, eE, eL);
+        } else {
+            bank_early_late(slot, c.f, tone1, lo, pw, on, fixE, eE, eL);
+        }
         if (c.live) {
             bank_timing(eE, eL, c.timing_freq, c.pos, g_fm);
             c.advance(st, mode, final_flag);
@@ -408,32 +419,40 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     }
     sm.flags[s] = kFlagExit;
     st_vol(&sm.exit_flag, 1);
-    bar_arrive<kBarO, 64>();  // the AFC warp waits for the next on-time correlations
+    if (ELB) bar_arrive<kBarWin, 64>();  // the AFC warp waits for the next window
+    else bar_arrive<kBarO, 64>();        // ... or for the next on-time correlations
     if (valid) c.persist(st, so, dstate, stream, counters);
     __syncthreads();  // (2)
 }
 
-template <int QX, int RING, int MINB>
+template <int QX, bool ELB, bool OB2>
 static cudaError_t launch_bank_t(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams, int mode,
                                  int final_flag, double afc_alpha, unsigned long long* counters, cudaStream_t st) {
-    const size_t smem = sizeof(BankSmem<RING>);
-    cudaError_t e = cudaFuncSetAttribute(demod_bank_kernel<QX, RING, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    // all of the SM's shared memory, or the resident CTAs the ring was sized for do not fit
-    e = cudaFuncSetAttribute(demod_bank_kernel<QX, RING, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             (int)cudaSharedmemCarveoutMaxShared);
+    const size_t smem = sizeof(BankSmem);
+    cudaError_t e = cudaFuncSetAttribute(demod_bank_kernel<QX, ELB, OB2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (n_streams + kSpc - 1) / kSpc;
-    demod_bank_kernel<QX, RING, MINB><<<grid, 96, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
+    demod_bank_kernel<QX, ELB, OB2><<<grid, 96, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
     return cudaGetLastError();
 }
-// Measured and dropped: more resident CTAs per SM through smaller rings and register caps
-// (RING 240/176/144 with 5/6/7 CTAs): a 176-row ring alone costs +36 % (too little prefetch distance for HBM latency),
-// a 112-register cap alone +23 %, and banks sized for 5-7 CTAs per SM ran slower in aggregate than two waves of four.
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// OPVD_BANK_QX / _ELB / _OB2: development switches (conversion split; early/late block sums on the AFC warp; on-time
+// blocks in two passes); results are identical
 cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                               cudaStream_t st) {
-    return launch_bank_t<1, 256, 4>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    static const int qx = env_int("OPVD_BANK_QX", 1), elb = env_int("OPVD_BANK_ELB", 0), ob2 = env_int("OPVD_BANK_OB2", 0);
+#define OPVD_BANK_CASE(Q, E, O) \
+    if (qx == Q && elb == E && ob2 == O)  \
+        return launch_bank_t<Q, E != 0, O != 0>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st)
+    OPVD_BANK_CASE(0, 0, 0); OPVD_BANK_CASE(2, 0, 0); OPVD_BANK_CASE(1, 1, 0);
+    OPVD_BANK_CASE(0, 0, 1); OPVD_BANK_CASE(1, 0, 1); OPVD_BANK_CASE(2, 0, 1);
+#undef OPVD_BANK_CASE
+    return launch_bank_t<1, false, false>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
 }
 
 }  // namespace opvd

@@ -165,8 +165,8 @@ size_t hostsim_demod_warp(const int16_t* iq, size_t n, int mode, double afc_alph
 
 // whole stream through the CHANNEL-BANK decomposition (demod_bank_core.cuh, kernels_demod_bank.cu): on-time sums of
 // both tones, early/late sums of the dominant tone only, LO powers from one zeta chain.  Same contract as hostsim_demod.
-static size_t demod_bank_impl(bool elb, const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
-                              double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
+size_t hostsim_demod_bank(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
+                          double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
     std::vector<uint32_t> w(n + 64 + 64, 0xDEADBEEFu);
     for (size_t i = 0; i < n; ++i)
         w[64 + i] = (uint32_t)(uint16_t)iq[2 * i] | ((uint32_t)(uint16_t)iq[2 * i + 1] << 16);
@@ -211,14 +211,7 @@ static size_t demod_bank_impl(bool elb, const int16_t* iq, size_t n, int mode, d
         cplx fixE = {0.0, 0.0};
         if (first) fixE = first_symbol_fix(win, f, tone1 ? lo.z1 : lo.z2);
         double eE, eL;
-        if (elb) {  // the AFC warp evaluates H0, H5 of both tones, the window warp combines the dominant tone's
-            BankElBlocks e;
-            bank_el_blocks(slot, lo.z1, lo.z2, e);
-            bank_early_late_from_blocks(f, tone1, lo, pw, on, tone1 ? e.H0a : e.H0b, tone1 ? e.H5a : e.H5b, e.s0, e.s60, fixE,
-                                        eE, eL);
-        } else {
-            bank_early_late(slot, f, tone1, lo, pw, on, fixE, eE, eL);
-        }
+        bank_early_late(slot, f, tone1, lo, pw, on, fixE, eE, eL);
         bank_timing(eE, eL, timing_freq, pos, g_fm);
         // AFC role
         bank_afc(afc, on.O1, on.O2, tone1, pw.zeta40, lo.inc1, lo.inc2, first, afc_alpha, g_fm);
@@ -239,97 +232,6 @@ static size_t demod_bank_impl(bool elb, const int16_t* iq, size_t n, int mode, d
     return ns;
 }
 
-size_t hostsim_demod_bank(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
-                          double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
-    return demod_bank_impl(false, iq, n, mode, afc_alpha, have_init, init_offset, soft_out, cap, est_out, final_freq, final_tfreq);
-}
-size_t hostsim_demod_bank_elb(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
-                              double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
-    return demod_bank_impl(true, iq, n, mode, afc_alpha, have_init, init_offset, soft_out, cap, est_out, final_freq, final_tfreq);
-}
-
-// the same through the FOUR-WARP kernel's decomposition (two window halves, kernels_demod_bank.cu demod_bank4_kernel)
-size_t hostsim_demod_bank4(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
-                           double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
-    std::vector<uint32_t> w(n + 64 + 64, 0xDEADBEEFu);
-    for (size_t i = 0; i < n; ++i)
-        w[64 + i] = (uint32_t)(uint16_t)iq[2 * i] | ((uint32_t)(uint16_t)iq[2 * i + 1] << 16);
-    const uint32_t* base = w.data() + 64;
-
-    DemodState st;
-    demod_state_init(st);
-    double est = 0.0;
-    if (mode == kModeBatch) {
-        est = hostsim_estimate(iq, n);
-        st.freq_offset = est;
-    } else if (have_init) {
-        st.freq_offset = init_offset;
-    } else if (n >= (size_t)kChunkSamples) {
-        est = hostsim_estimate(iq, kChunkSamples);
-        st.freq_offset = est;
-    }
-    st.flags |= kFlagEstDone;
-    BankAfc afc = {st.freq_offset, st.ph1, st.ph2, st.p1, st.p2};
-    BankLo lo;
-    BankPow pw;
-    {
-        double d;
-        const cplx zeta = bank_zeta_general(afc.freq_offset, d);
-        bank_lo_from_zeta(zeta, d, lo, g_fm);
-        bank_pow_from_zeta(zeta, pw, g_bk);
-    }
-    double pos = st.pos, timing_freq = st.timing_freq;
-    size_t ns = 0;
-    while (demod_schedule(st, pos, mode, (int64_t)n, true)) {
-        const int64_t b = (int64_t)pos;
-        const double f = pos - (double)b;
-        const uint32_t* win = base + st.origin + b - kWinLead;
-        const bool first = st.sym_in_call == 0;
-        auto slot = [&](int k, double& I, double& Q) { unpack_iq(win[k], I, Q); };
-        // LO warp: H1, H2; HI warp: H3, H4, s50
-        cplx A[2], B[2], Cc[2], D[2], s10, s20, s30, s40, s50;
-        bank_two_blocks(slot, 10, lo.z1, lo.z2, A, B, s10, s20);
-        bank_two_blocks(slot, 30, lo.z1, lo.z2, Cc, D, s30, s40);
-        slot(50, s50.r, s50.i);
-        const cplx P1 = cfma(pw.q1, A[1], A[0]), P2 = cfma(pw.q2, B[1], B[0]);
-        const cplx R1 = cfma(pw.q1, Cc[1], Cc[0]), R2 = cfma(pw.q2, D[1], D[0]);
-        cplx O1, O2;
-        double eO1, eO2;
-        bank_on_time_from_halves(f, lo, pw, P1, P2, R1, R2, s10, s50, O1, O2, eO1, eO2);
-        const bool tone1 = eO1 > eO2;
-        const double soft = eO2 - eO1;
-        // HI warp: H5 of both tones, late gate
-        cplx H5a, H5b, s60;
-        bank_block_both(slot, 50, lo.z1, lo.z2, H5a, H5b);
-        slot(60, s60.r, s60.i);
-        const cplx zd = tone1 ? lo.z1 : lo.z2, qd = tone1 ? pw.q1 : pw.q2, qqd = tone1 ? pw.qq1 : pw.qq2;
-        const cplx z40 = bank_z40(pw.zeta40, tone1 ? 0 : 1);
-        const double eL = bank_gate_energy(f, zd, qd, qqd, z40, tone1 ? A[1] : B[1], tone1 ? R1 : R2, tone1 ? H5a : H5b, s60,
-                                           s20, cplx{0.0, 0.0});
-        // LO warp: H0 of the dominant tone, early gate, timing
-        cplx fixE = {0.0, 0.0};
-        if (first) fixE = first_symbol_fix(win, f, zd);
-        cplx H0, s0;
-        bank_block_one(slot, 0, zd, H0, s0);
-        const double eE = bank_gate_energy(f, zd, qd, qqd, z40, H0, tone1 ? P1 : P2, tone1 ? Cc[0] : D[0], s40, s0, fixE);
-        bank_timing(eE, eL, timing_freq, pos, g_fm);
-        bank_afc(afc, O1, O2, tone1, pw.zeta40, lo.inc1, lo.inc2, first, afc_alpha, g_fm);
-        if (!first) {
-            double d;
-            const cplx zeta = bank_zeta_fast(afc.freq_offset, d, g_fm);
-            bank_lo_from_zeta(zeta, d, lo, g_fm);
-            bank_pow_from_zeta(zeta, pw, g_bk);
-        }
-        st.sym_in_call++;
-        if (ns < cap) soft_out[ns] = soft;
-        ++ns;
-        st.n_sym++;
-    }
-    if (est_out) *est_out = est;
-    if (final_freq) *final_freq = afc.freq_offset;
-    if (final_tfreq) *final_tfreq = timing_freq;
-    return ns;
-}
 
 // coherent mode (-c, batch only) through demod_coherent_core.cuh.  Returns number of soft symbols.
 size_t hostsim_demod_coherent(const int16_t* iq, size_t n, double afc_alpha, double pll_bw, double* soft_out, size_t cap,
