@@ -314,7 +314,7 @@ def tot_streams(S, world, dev, reduce_counters):
     return reduce_counters({"s": S}, dev)["s"] if world > 1 else S
 
 
-def run_sustained(args, pkg, torch, np, dev, local_rank, S, bank_buf, barrier, reduce_max_ms):
+def run_sustained(args, pkg, torch, np, dev, local_rank, world, S, bank_buf, barrier, reduce_max_ms):
     """A bank larger than HBM end to end: S streams fed from pinned host memory in one-frame time tiles through
     push / run / poll with persistent state (sample and soft-symbol rings, no copies on the device).  The host tile
     (frame 1 of every stream, frame-aligned) is pushed over and over, so every stream is a continuous periodic
@@ -352,9 +352,10 @@ def run_sustained(args, pkg, torch, np, dev, local_rank, S, bank_buf, barrier, r
     n_frames = sum(f.data.shape[0] for f in frames)
     out = {"workload": f"{S} streams x {T} one-frame tiles per GPU from pinned host memory ({S * FRAME_SAMPLES * 4 * T / 1e9:.0f} GB "
                        f"through a {S * 3 * FRAME_SAMPLES * 4 / 1e9:.1f} GB device ring), poll every 4 tiles",
-           "value": round(S * FRAME_SAMPLES * T / el / 1e6, 2), "unit": UNIT, "seconds": round(el, 3),
-           "h2d_bytes": int(S * FRAME_SAMPLES * 4 * T), "d2h_bytes": d2h, "frames": n_frames, "frames_lost": lost,
-           "h2d_gbs": round(S * FRAME_SAMPLES * 4 * T / el / 1e9, 2)}
+           "value": round(world * S * FRAME_SAMPLES * T / el / 1e6, 2), "unit": UNIT, "seconds": round(el, 3),
+           "value_note": "whole job (all ranks; every rank feeds its own bank from its own pinned buffer)",
+           "h2d_bytes_per_gpu": int(S * FRAME_SAMPLES * 4 * T), "d2h_bytes_rank0": d2h, "frames_rank0": n_frames,
+           "frames_lost": lost, "h2d_gbs": round(world * S * FRAME_SAMPLES * 4 * T / el / 1e9, 2)}
     # parity on a sample of streams against the reference binary on the same (periodic) bytes
     if int(os.environ.get("RANK", "0")) == 0:
         from oracle import oracle as ora
@@ -583,7 +584,7 @@ def main():
         channel_bank["scaling"] = "weak"
         if not args.no_sustained:
             bbank.close()
-            channel_bank["sustained"] = run_sustained(args, pkg, torch, np, dev, local_rank, Sb, bbuf, barrier, reduce_max_ms)
+            channel_bank["sustained"] = run_sustained(args, pkg, torch, np, dev, local_rank, world, Sb, bbuf, barrier, reduce_max_ms)
         else:
             bbank.close()
         del bbuf

@@ -18,6 +18,9 @@ namespace opvd {
 //     i in steps of 4: 4 x-samples and 7 y-samples in registers feed 16 products, i.e. 0.5 shared
 //     loads per product instead of 2.  Tile t needs 10 - t steps, so every role does 11 steps.
 //   * blocks are zero-padded to 44 samples, so products that reach past the block need no mask.
+// Integer accumulation (one IMAD.WIDE s32 x s32 + s64 per product instead of one DFMA) was measured in round 2 and is
+// slower on B200: 12.0 ms against 8.4 ms for 18,944 streams.  The 64-bit integer multiply-add issues at a lower rate
+// than the FP64 pipe's DFMA.
 constexpr int kEstSlots = 32;                 // blocks per pass
 constexpr int kEstRoles = 5;
 constexpr int kEstThreads = kEstSlots * kEstRoles;   // 160

@@ -10,6 +10,7 @@ ap.add_argument("--frames", type=int, default=25)
 ap.add_argument("--mode", default="stream")
 ap.add_argument("--lanes", type=int, default=0)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--tiles", type=int, default=1, help="time tiles per pass (attach a growing prefix, run each)")
 ap.add_argument("--ebn0", type=float, nargs=2, default=[2.0, 10.0])
 a = ap.parse_args()
 S, nf = a.streams, a.frames
@@ -21,9 +22,18 @@ t0 = time.time(); pkg.synth_bank(buf.data_ptr(), sp); torch.cuda.synchronize(); 
 print(f"synth {S}x{n} samples ({S*n*4/1e9:.2f} GB) in {t1-t0:.2f}s", flush=True)
 for rep in range(a.reps):
     bank = pkg.DemodBank(S, streaming=(a.mode == "stream"), lanes_per_stream=a.lanes)
-    bank.attach_device_iq(buf.data_ptr(), stride, n, keepalive=buf)
-    t0 = time.time(); bank.run(final=True); t1 = time.time()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    if a.tiles <= 1:
+        bank.attach_device_iq(buf.data_ptr(), stride, n, keepalive=buf)
+        bank.run(final=True)
+    else:
+        for t in range(a.tiles):
+            avail = n if t == a.tiles - 1 else (t + 1) * n // a.tiles
+            bank.attach_device_iq(buf.data_ptr(), stride, avail, keepalive=buf)
+            bank.run(final=(t == a.tiles - 1), sync=False)
     ms = bank.last_run_ms(); c = bank.counters()
+    t1 = time.time()
     tot = ms["total"] / 1e3
     print(json.dumps({"rep": rep, "S": S, "frames": nf, "ms": ms, "wall_s": round(t1 - t0, 4),
                       "Msps": round(S * n / tot / 1e6, 1), "GBps": round(S * n * 4 / tot / 1e9, 1),
