@@ -104,19 +104,20 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], None, set()
+        sm, smax, reasons, pw = [], None, set(), []
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 smax = float(r[1])
+                pw.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except (ValueError, IndexError):
                 pass
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def measured_peaks():
@@ -266,6 +267,8 @@ def run_bank_leg(args, pkg, torch, dev, local_rank, world, S, first_stream, n_fr
     ends = tile_ends(n, n_frames, tiles)
     steps, warm = max(2, min(args.steps, 3)), 3
     per = {"estimate": 0.0, "demod": 0.0, "track": 0.0, "decode": 0.0, "total": 0.0}
+    sampler = ClockSampler(local_rank)  # this leg loads every SM's FP64 pipe: the clocks it ran at belong to its numbers
+    sampler.start()
     for _ in range(warm):
         tiled_step(bank, buf.data_ptr(), stride, ends, buf)
     barrier()
@@ -274,6 +277,7 @@ def run_bank_leg(args, pkg, torch, dev, local_rank, world, S, first_stream, n_fr
         for k in per:
             per[k] += ms[k]
     barrier()
+    leg_clocks = sampler.stop()
     c = bank.counters()
     bank.bert_check(sp)
     ber = bank.counters()
@@ -300,6 +304,7 @@ def run_bank_leg(args, pkg, torch, dev, local_rank, world, S, first_stream, n_fr
                      "traffic": _traffic(load_profile_json("roofline_traffic.json"), bank.demod_variant(), c["samples"] * 4)},
         "note": "total is the elapsed device time of the step: tracker + Viterbi of tile t overlap the demodulator of "
                 "tile t+1, the estimate (first 40,000 samples of every stream) runs once in the first tile",
+        "clocks": leg_clocks,
     }
     if mb:
         dfma = c["samples"] * 12.0 / (demod_ms * 1e-3)
