@@ -3,7 +3,7 @@
 # command, memcheck over both demodulator kernels.  Tight timeouts; stop at the first hang.
 set -x -o pipefail
 mkdir -p gpurun_out
-TAG=r02_h
+TAG=${1:-r02_h}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv
 nproc
 timeout 60 python tools/probe.py --streams 4096 --frames 3 --reps 1 --lanes 96 2>&1 | tail -1 | cut -c1-200 || exit 1
@@ -18,6 +18,6 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 grep -c . gpurun_out/launches_$TAG.csv
 export PATH=/usr/local/cuda/bin:$PATH
 for L in 96 32; do
-  timeout 240 compute-sanitizer --tool memcheck --print-limit 5 python tools/probe.py --streams 80 --frames 2 --reps 1 --lanes $L > gpurun_out/memcheck_r02_$L.log 2>&1
-  echo "memcheck lanes=$L: $(grep -E 'ERROR SUMMARY' gpurun_out/memcheck_r02_$L.log)"
+  timeout 240 compute-sanitizer --tool memcheck --print-limit 5 python tools/probe.py --streams 80 --frames 2 --reps 1 --lanes $L > gpurun_out/memcheck_${TAG}_$L.log 2>&1
+  echo "memcheck lanes=$L: $(grep -E 'ERROR SUMMARY' gpurun_out/memcheck_${TAG}_$L.log)"
 done
