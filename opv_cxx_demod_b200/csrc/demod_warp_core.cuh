@@ -104,16 +104,20 @@ struct LanePartial {
     cplx W, F;
 };
 
-// s[0..4]: packed raw samples of this lane's slots c..c+4
-OPVD_HD LanePartial warp_lane_partial(const WarpLane& w, const uint32_t* s) {
-    double I[5], Q[5];
-#pragma unroll
-    for (int r = 0; r < 5; ++r) unpack_iq(s[r], I[r], Q[r]);
+// I[0..4], Q[0..4]: samples of this lane's slots c..c+4
+OPVD_HD LanePartial warp_lane_partial_d(const WarpLane& w, const double* I, const double* Q) {
     const cplx G = horner5(I, Q, w.z);
     LanePartial o;
     o.W = cmul(w.R, G);
     o.F = {fma(w.R.r, I[0], -(w.R.i * Q[0])), fma(w.R.r, Q[0], w.R.i * I[0])};
     return o;
+}
+// s[0..4]: the same samples packed
+OPVD_HD LanePartial warp_lane_partial(const WarpLane& w, const uint32_t* s) {
+    double I[5], Q[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) unpack_iq(s[r], I[r], Q[r]);
+    return warp_lane_partial_d(w, I, Q);
 }
 
 // LO step and slot rotation in the hot loop: valid for |freq_offset| <= 2.2 kHz, which the AFC clamp

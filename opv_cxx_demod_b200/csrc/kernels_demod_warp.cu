@@ -114,21 +114,27 @@ struct WarpCtx {
         cp_async_wait<0>();
         __syncwarp();
     }
-    __device__ __forceinline__ void load_window(int b, uint32_t (&s5)[5]) const {
+    // this lane's five samples of the window at integer position b, converted: the conversions (XU pipe, 8 cycles per
+    // warp instruction, ten per symbol) run where they are issued, in the shadow of the AFC chain of the previous symbol,
+    // not at the head of the next one where the Horner chain would wait for them
+    __device__ __forceinline__ void load_window(int b, double (&I5)[5], double (&Q5)[5]) const {
         const uint32_t* src = ring + (((origin_rel + b - kWinLead) & kRingMask) + lane_slot);
+        uint32_t s5[5];
 #pragma unroll
         for (int r = 0; r < 5; ++r) s5[r] = src[r];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) unpack_iq(s5[r], I5[r], Q5[r]);
     }
 
-    // One symbol at integer position b = trunc(pos), whose five lane samples are already in s5.
-    // Updates pos, then loads the NEXT symbol's samples into s5 and returns its b, before running the
+    // One symbol at integer position b = trunc(pos), whose five lane samples are already in I5/Q5.
+    // Updates pos, then loads the NEXT symbol's samples into I5/Q5 and returns its b, before running the
     // AFC chain, so that the loads and the AFC arithmetic overlap.  FIRST: first symbol of a
     // demodulate() call (early-gate clamp :237, no AFC update :289).
     template <bool FIRST>
-    __device__ __forceinline__ int symbol(int b, uint32_t (&s5)[5]) {
+    __device__ __forceinline__ int symbol(int b, double (&I5)[5], double (&Q5)[5]) {
         const double f = pos - (double)b;
         // ---- lane partial sums over this lane's five slots
-        const LanePartial lp = warp_lane_partial(wl, s5);
+        const LanePartial lp = warp_lane_partial_d(wl, I5, Q5);
 
         // ---- gate sums: 8 consecutive lanes via shuffle-down 1, 2, 4; edge term from lane p+8
         const cplx Fh = shfl_down_c(lp.F, 8);
@@ -158,7 +164,7 @@ struct WarpCtx {
 
         // ---- next symbol's samples (its window is already in the ring, see ring_maintain)
         const int b_next = __double2int_rz(pos);  // pos >= 0: truncation == floor (:125)
-        load_window(b_next, s5);
+        load_window(b_next, I5, Q5);
 
         // ---- AFC on the on-time gate lanes (:289-307)
         const bool x_zero = nrm == 0.0;
@@ -229,12 +235,12 @@ demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         const int call_len_i = (int)st.call_len;
         const double call_len_d = (double)st.call_len;
         int b = __double2int_rz(c.pos);  // pos >= 0: truncation == floor (:125)
-        uint32_t s5[5];
+        double I5[5], Q5[5];
         if (c.issued_s < 0) c.ring_prime(c.origin_rel + b - kWinLead);  // first symbol of this launch
         else c.ring_maintain(c.origin_rel + b - kWinLead);
-        c.load_window(b, s5);
+        c.load_window(b, I5, Q5);
         if (st.sym_in_call == 0) {
-            b = c.symbol<true>(b, s5);
+            b = c.symbol<true>(b, I5, Q5);
             st.sym_in_call = 1;
             if (!((c.pos + 40.0) + 10.0 < call_len_d)) continue;
         }
@@ -242,7 +248,7 @@ demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         for (;;) {
             if (b + 52 >= call_len_i && !((c.pos + 40.0) + 10.0 < call_len_d)) break;
             c.ring_maintain(c.origin_rel + b - kWinLead);
-            b = c.symbol<false>(b, s5);
+            b = c.symbol<false>(b, I5, Q5);
         }
         st.sym_in_call = 2;  // any non-zero value: the open call has produced symbols
     }

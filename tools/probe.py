@@ -11,6 +11,7 @@ ap.add_argument("--mode", default="stream")
 ap.add_argument("--lanes", type=int, default=0)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--tiles", type=int, default=1, help="time tiles per pass (attach a growing prefix, run each)")
+ap.add_argument("--tile-frames", default="", help="comma-separated frame counts at which the time tiles end (overrides --tiles)")
 ap.add_argument("--ebn0", type=float, nargs=2, default=[2.0, 10.0])
 a = ap.parse_args()
 S, nf = a.streams, a.frames
@@ -24,7 +25,12 @@ for rep in range(a.reps):
     bank = pkg.DemodBank(S, streaming=(a.mode == "stream"), lanes_per_stream=a.lanes)
     torch.cuda.synchronize()
     t0 = time.time()
-    if a.tiles <= 1:
+    if a.tile_frames:
+        ends = [4000 + 86720 * int(x) for x in a.tile_frames.split(",")] + [n]
+        for k, e in enumerate(ends):
+            bank.attach_device_iq(buf.data_ptr(), stride, e, keepalive=buf)
+            bank.run(final=(k == len(ends) - 1), sync=False)
+    elif a.tiles <= 1:
         bank.attach_device_iq(buf.data_ptr(), stride, n, keepalive=buf)
         bank.run(final=True)
     else:
