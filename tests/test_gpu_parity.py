@@ -631,7 +631,8 @@ def test_baseline_config3_long_captures_random_starts_and_dropouts(pkg, ora):
 def test_baseline_config1_full_length_streams_vs_reference_binary(pkg, ora):
     """BASELINE.json configs[1] at its real capture length: 64 streams x 10 s (250 frames, 21.7 M samples each) with AWGN
     2..10 dB, each demodulated in full by the UNMODIFIED reference binary (one process per stream, host cores in
-    parallel) and by the GPU chain in time tiles; frame count and every byte of every stream must agree."""
+    parallel) and by the GPU chain in time tiles, through both demodulator kernels; frame count and every byte of every
+    stream must agree."""
     import torch
 
     if not os.path.exists(ora.REF_DEMOD):
@@ -642,25 +643,27 @@ def test_baseline_config1_full_length_streams_vs_reference_binary(pkg, ora):
     buf = torch.zeros((S, stride), dtype=torch.int32, device="cuda")
     sp = pkg.make_synth(S, n_frames, stride, n, seed=31, ebn0_lo_db=2.0, ebn0_hi_db=10.0, max_lead=4000)
     pkg.synth_bank(buf.data_ptr(), sp)
-    bank = pkg.DemodBank(S, streaming=True)
-    for e in list(range(25 * 86720, n, 25 * 86720)) + [n]:      # ten time tiles, runs queued ahead
-        bank.attach_device_iq(buf.data_ptr(), stride, e, keepalive=buf)
-        bank.run(final=(e == n), sync=False)
-    fr = bank.poll_frames()
     host = buf[:, :n].cpu().numpy().view(np.int16).reshape(S, n, 2)
     outs = _ref_binary_many(ora, [host[k] for k in range(S)], ["-s", "-r", "-q"])
-    for s in range(S):
-        ref = np.frombuffer(outs[s], np.uint8).reshape(-1, 134)
-        got = fr.of_stream(s)
-        assert got.shape == ref.shape and np.array_equal(got, ref), (s, got.shape, ref.shape)
-    assert fr.data.shape[0] > 0.5 * S * n_frames
-    bank.close()
+    for lanes in (32, 96):                                          # both demodulator kernels on the same bytes
+        bank = pkg.DemodBank(S, streaming=True, lanes_per_stream=lanes)
+        for e in list(range(25 * 86720, n, 25 * 86720)) + [n]:      # ten time tiles, runs queued ahead
+            bank.attach_device_iq(buf.data_ptr(), stride, e, keepalive=buf)
+            bank.run(final=(e == n), sync=False)
+        fr = bank.poll_frames()
+        for s in range(S):
+            ref = np.frombuffer(outs[s], np.uint8).reshape(-1, 134)
+            got = fr.of_stream(s)
+            assert got.shape == ref.shape and np.array_equal(got, ref), (lanes, s, got.shape, ref.shape)
+        assert fr.data.shape[0] > 0.5 * S * n_frames
+        bank.close()
 
 
 def test_baseline_config3_true_length_60s_vs_reference_binary(pkg, ora):
     """BASELINE.json configs[3] at its real length: 8 streams x 60 s (1,500 frames, 130 M samples each: sample positions
     and symbol counts deep into the range where FP32 or 32-bit indexing would break) with random frame starts and
-    dropouts shorter and longer than the 5-miss flywheel limit (:60), whole streams against the reference binary."""
+    dropouts shorter and longer than the 5-miss flywheel limit (:60), whole streams against the reference binary, through
+    both demodulator kernels."""
     import torch
 
     from tools import captures as cap
@@ -692,20 +695,21 @@ def test_baseline_config3_true_length_60s_vs_reference_binary(pkg, ora):
     for k, c in enumerate(caps):
         buf[k, :c.shape[0]] = torch.from_numpy(np.ascontiguousarray(c).view(np.int32).reshape(-1)).cuda()
     lens = np.array([c.shape[0] for c in caps], np.int64)
-    bank = pkg.DemodBank(S, streaming=True)
-    bank.attach_device_iq(buf.data_ptr(), stride, lens, keepalive=buf)
-    bank.run(final=True)
-    fr = bank.poll_frames()
     outs = _ref_binary_many(ora, caps, ["-s", "-r", "-q"])
-    lost = 0
-    for s in range(S):
-        ref = np.frombuffer(outs[s], np.uint8).reshape(-1, 134)
-        got = fr.of_stream(s)
-        assert got.shape == ref.shape and np.array_equal(got, ref), (s, got.shape, ref.shape)
-        assert bank.stream_info(s)["n_samples_used"] > 129_000_000
-        lost += sum(1 for (t, _, _, _, _) in bank.poll_events(s) if t == 5)
-    assert lost >= 8
-    bank.close()
+    for lanes in (32, 96):                                      # both demodulator kernels on the same bytes
+        bank = pkg.DemodBank(S, streaming=True, lanes_per_stream=lanes)
+        bank.attach_device_iq(buf.data_ptr(), stride, lens, keepalive=buf)
+        bank.run(final=True)
+        fr = bank.poll_frames()
+        lost = 0
+        for s in range(S):
+            ref = np.frombuffer(outs[s], np.uint8).reshape(-1, 134)
+            got = fr.of_stream(s)
+            assert got.shape == ref.shape and np.array_equal(got, ref), (lanes, s, got.shape, ref.shape)
+            assert bank.stream_info(s)["n_samples_used"] > 129_000_000
+            lost += sum(1 for (t, _, _, _, _) in bank.poll_events(s) if t == 5)
+        assert lost >= 8
+        bank.close()
 
 
 def test_abi_error_behaviour(pkg):
