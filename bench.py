@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--tiles", type=int, default=10, help="time tiles per step of the headline leg")
     ap.add_argument("--e2e-seconds", type=float, default=0.52, help="capture length per stream for the e2e leg")
     ap.add_argument("--e2e-tiles", type=int, default=8, help="time tiles per e2e step (H2D of a tile overlaps the kernels of the previous one)")
+    ap.add_argument("--e2e-ring-tiles", type=int, default=2, help="device ring of the e2e leg, in tiles (+ one frame of carry)")
     ap.add_argument("--bank-streams", type=int, default=0,
                     help="streams per GPU of the channel-bank leg (0 = 4 CTAs x 32 streams per SM, 18,944 on a B200)")
     ap.add_argument("--bank-frames", type=int, default=14, help="frames per stream of the channel-bank legs")
@@ -505,7 +506,7 @@ def main():
         cuts = [n_e * t // tiles // 64 * 64 for t in range(tiles)] + [n_e]
         tile_max = max(cuts[t + 1] - cuts[t] for t in range(tiles))
         # device ring of two tiles + one chunk of carry: tile t+1 crosses PCIe while the kernels of tile t run
-        ebank = pkg.DemodBank(S, streaming=True, device=local_rank, max_samples=2 * tile_max + FRAME_SAMPLES + 256,
+        ebank = pkg.DemodBank(S, streaming=True, device=local_rank, max_samples=args.e2e_ring_tiles * tile_max + FRAME_SAMPLES + 256,
                               lanes_per_stream=args.lanes)
         d2h = 0
 
@@ -540,15 +541,36 @@ def main():
         c_s = reduce_max_ms(time.perf_counter() - t0, dev)
         h2d_ceiling = S * n_e * 4 * reps_c * world / c_s / 1e9
         del dst
+        # the same tile-shaped pushes through the ABI into a buffer that holds the whole capture, with no run between
+        # them: what the copies alone achieve in the shape the e2e leg issues them (1,024 rows per tile, pitched)
+        cbank = pkg.DemodBank(S, streaming=True, device=local_rank, max_samples=n_e + 256, lanes_per_stream=args.lanes)
+
+        def push_only():
+            cbank.reset()
+            for t in range(tiles):
+                cbank.push_iq_host_ptr(host.data_ptr() + 4 * cuts[t], cuts[t + 1] - cuts[t], n_e)
+            cbank.sync()
+
+        push_only()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps_c):
+            push_only()
+        barrier()
+        p_s = reduce_max_ms(time.perf_counter() - t0, dev)
+        h2d_tiled = S * n_e * 4 * reps_c * world / p_s / 1e9
+        cbank.close()
         e2e = {"value": round(e_val, 2), "unit": UNIT, "h2d_bytes_per_step": int(S * n_e * 4), "d2h_bytes_per_step": d2h,
                "sample": f"{S} streams x {nf_e} frames ({n_e} samples) per rank per step from pinned host memory, "
-                         f"pushed and run in {tiles} time tiles through a {2 * tile_max + FRAME_SAMPLES + 256}-sample device ring "
+                         f"pushed and run in {tiles} time tiles through a {args.e2e_ring_tiles * tile_max + FRAME_SAMPLES + 256}-sample device ring "
                          f"per stream; the rate is bound by the host-to-device copies ({S * n_e * 4 * args.steps / e_s / 1e9:.1f} GB/s "
                          f"per GPU), so it does not depend on the capture length",
                "frames_per_step": int(fr.data.shape[0]),
                "h2d_gbs": round(S * world * n_e * 4 * args.steps / e_s / 1e9, 2),
                "h2d_ceiling_gbs": round(h2d_ceiling, 2),
                "frac_of_h2d_ceiling": round(S * world * n_e * 4 * args.steps / e_s / 1e9 / h2d_ceiling, 4),
+               "h2d_tiled_push_gbs": round(h2d_tiled, 2),
+               "h2d_tiled_push_note": "the same opvd_push_iq_all calls with no run between them (copies only)",
                "h2d_ceiling_note": "all ranks copying the same pinned buffers at once with plain cudaMemcpyAsync, no kernels; "
                                    "on this box every GPU hangs off NUMA node 0, so the ceiling itself does not scale "
                                    "linearly with the rank count"}

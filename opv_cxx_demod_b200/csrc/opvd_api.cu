@@ -57,7 +57,8 @@ struct opvd_handle {
     int64_t stride = 0;
     bool ring = false, attached = false;
     std::vector<int64_t> h_avail;    // host truth: samples pushed / attached per stream
-    int64_t* h_snap = nullptr;       // pinned [kRuns][S]: avail as seen by each run
+    int64_t* h_snap = nullptr;       // pinned + mapped [kRuns][S]: avail as seen by each run
+    int64_t* h_snap_dev = nullptr;   // the same memory as the device sees it
     int64_t* d_avail = nullptr;      // [kRuns][S]
 
     // runs
@@ -68,6 +69,10 @@ struct opvd_handle {
     int64_t run_syms[kRuns]{};       // bound on the soft symbols each run can have produced
     double acc_ms[4]{};              // estimate, demod, track, decode since the last reset
     cudaEvent_t ev_first = nullptr, ev_last = nullptr;
+    // OPVD_TRACE=1 (development aid): timeline of the pushes and runs since the last reset, printed by opvd_poll_frames
+    bool trace = false;
+    std::vector<cudaEvent_t> tr_c0, tr_c1;  // begin / end of every push on the copy stream
+    int tr_n = 0;
     bool have_first = false, have_times = false;
 
     // per-stream state
@@ -142,6 +147,15 @@ __global__ void init_state_kernel(DemodState* d, TrackState* t, double* est, int
     est[i] = 0.0;
     nsym[i] = 0;
     nsym[n + i] = 0;
+}
+
+// A run's per-stream sample counts go from the pinned snapshot to the device through a KERNEL that reads the host
+// memory directly, not through cudaMemcpyAsync: on the copy engine an 8-byte-per-stream copy queues behind the next
+// tile's 10 ms push (the engine arbitrates between streams, not by age), and the run that needs it starts one tile late
+// (measured with OPVD_TRACE: the e2e leg lost 2-3 ms of PCIe time per tile to it).
+__global__ void snapshot_kernel(int64_t* __restrict__ dst, const int64_t* __restrict__ src_host, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src_host[i];
 }
 
 bool stream_ring(const opvd_handle* h) { return h->cfg.mode == OPVD_MODE_STREAM && !h->attached; }
@@ -237,6 +251,11 @@ int opvd_create(const opvd_config* cfg, opvd_handle** out) {
         !ok(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming)) || !ok(cudaEventCreate(&h->ev_first)) ||
         !ok(cudaEventCreate(&h->ev_last)))
         return fail(OPVD_ERR_CUDA);
+    h->trace = getenv("OPVD_TRACE") != nullptr;
+    if (h->trace) {
+        h->tr_c0.resize(64); h->tr_c1.resize(64);
+        for (int i = 0; i < 64; ++i) { cudaEventCreate(&h->tr_c0[i]); cudaEventCreate(&h->tr_c1[i]); }
+    }
     for (int r = 0; r < kRuns; ++r) {
         if (!ok(cudaEventCreateWithFlags(&h->ev_front[r], cudaEventDisableTiming)) ||
             !ok(cudaEventCreateWithFlags(&h->ev_back[r], cudaEventDisableTiming)))
@@ -249,7 +268,8 @@ int opvd_create(const opvd_config* cfg, opvd_handle** out) {
         !ok(dalloc(&h->d_avail, (size_t)kRuns * h->S)) || !ok(dalloc(&h->d_nsym, (size_t)2 * h->S)) ||
         !ok(dalloc(&h->d_nevents, h->S)) || !ok(dalloc(&h->d_ntasks, 1)) || !ok(dalloc(&h->d_counters, kNumCounters)) ||
         !ok(dalloc(&h->d_log_count, 1)) ||
-        !ok(cudaMallocHost(reinterpret_cast<void**>(&h->h_snap), sizeof(int64_t) * kRuns * h->S)) ||
+        !ok(cudaHostAlloc(reinterpret_cast<void**>(&h->h_snap), sizeof(int64_t) * kRuns * h->S, cudaHostAllocMapped)) ||
+        !ok(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->h_snap_dev), h->h_snap, 0)) ||
         !ok(cudaMallocHost(reinterpret_cast<void**>(&h->h_log_count), sizeof(unsigned long long))))
         return fail(OPVD_ERR_CUDA);
     *h->h_log_count = 0;
@@ -319,6 +339,7 @@ int opvd_reset(opvd_handle* h) {
     CK(cudaMemsetAsync(h->d_log_count, 0, sizeof(unsigned long long), h->st));
     if (h->d_metrics)
         CK(cudaMemsetAsync(h->d_metrics, 0xFF, (size_t)h->S * h->max_frames * sizeof(int32_t), h->st));
+    h->tr_n = 0;
     *h->h_log_count = 0;
     h->polled_log = 0;
     h->lost_frames = 0;
@@ -351,7 +372,7 @@ static int push_common(opvd_handle* h, int32_t first, int32_t count, const int16
     };
     long long need = -2;  // run whose demodulator must have finished before the copy may start; -1: none
     for (int attempt = 0; attempt < 2 && need == -2; ++attempt) {
-        if (h->run_seq == 0) {
+        if (h->run_seq == 0 || fits(-1)) {  // room without anything retiring: no wait
             if (fits(-1)) need = -1;
         } else {
             for (long long r = std::max<long long>(0, h->run_seq - kRuns); r < h->run_seq; ++r)
@@ -370,6 +391,7 @@ static int push_common(opvd_handle* h, int32_t first, int32_t count, const int16
     }
     if (need == -2) return OPVD_ERR_CAPACITY;
     if (need >= 0) CK(cudaStreamWaitEvent(h->st_copy, h->ev_front[need % kRuns], 0));
+    if (h->trace && h->tr_n < (int)h->tr_c0.size()) CK(cudaEventRecord(h->tr_c0[h->tr_n], h->st_copy));
     // ---- copy, in two pieces where the ring wraps
     bool uniform = true;
     for (int s = first; s < first + count; ++s) uniform = uniform && h->h_avail[s] == h->h_avail[first];
@@ -397,6 +419,7 @@ static int push_common(opvd_handle* h, int32_t first, int32_t count, const int16
     }
     // the next opvd_run waits for this event on the device before its kernels read the samples
     CK(cudaEventRecord(h->ev_copy, h->st_copy));
+    if (h->trace && h->tr_n < (int)h->tr_c0.size()) CK(cudaEventRecord(h->tr_c1[h->tr_n++], h->st_copy));
     h->copy_pending = true;
     for (int s = first; s < first + count; ++s) h->h_avail[s] += n;
     return OPVD_OK;
@@ -465,7 +488,7 @@ int opvd_run(opvd_handle* h, int final_flag) {
     int64_t* snap = h->h_snap + (size_t)slot * h->S;
     std::copy(h->h_avail.begin(), h->h_avail.end(), snap);
     int64_t* d_avail = h->d_avail + (size_t)slot * h->S;
-    CK(cudaMemcpyAsync(d_avail, snap, sizeof(int64_t) * h->S, cudaMemcpyHostToDevice, h->st));
+    snapshot_kernel<<<(h->S + 255) / 256, 256, 0, h->st>>>(d_avail, h->h_snap_dev + (size_t)slot * h->S, h->S);
     if (h->copy_pending) {  // pushed samples must have landed before the kernels read them (device-side wait)
         CK(cudaStreamWaitEvent(h->st, h->ev_copy, 0));
         h->copy_pending = false;
@@ -557,6 +580,21 @@ int opvd_poll_frames(opvd_handle* h, int32_t max_frames, uint8_t* frames134, opv
     if (!h->d_log) return 0;
     // ---- fetch what the runs enqueued so far have logged since the last poll
     if (h->run_seq > 0) CK(cudaEventSynchronize(h->ev_back[(h->run_seq - 1) % kRuns]));
+    if (h->trace && h->tr_n > 0 && h->run_seq > 0 && h->run_seq <= kRuns) {
+        CK(cudaStreamSynchronize(h->st_copy));
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < h->tr_n; ++i) {
+            cudaEventElapsedTime(&a, h->tr_c0[0], h->tr_c0[i]);
+            cudaEventElapsedTime(&b, h->tr_c0[0], h->tr_c1[i]);
+            fprintf(stderr, "opvd trace: push %d copy %.2f .. %.2f ms\n", i, a, b);
+        }
+        for (long long r = 0; r < h->run_seq; ++r) {
+            float t[5];
+            for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], h->tr_c0[0], h->ev_t[r % kRuns][i]);
+            fprintf(stderr, "opvd trace: run %lld front %.2f est %.2f demod %.2f | back track %.2f decode %.2f ms\n", r, t[0], t[1], t[2], t[3], t[4]);
+        }
+        h->tr_n = 0;
+    }
     const unsigned long long total = *h->h_log_count;
     if (total - h->polled_log > (unsigned long long)h->log_cap) {  // the log wrapped over frames nobody polled
         const unsigned long long lost = total - h->polled_log - (unsigned long long)h->log_cap;
