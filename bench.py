@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=0, help="demodulator kernel variant (0 = automatic)")
     ap.add_argument("--tiles", type=int, default=10, help="time tiles per step of the headline leg")
     ap.add_argument("--e2e-seconds", type=float, default=0.52, help="capture length per stream for the e2e leg")
-    ap.add_argument("--e2e-tiles", type=int, default=8, help="time tiles per e2e step (H2D of a tile overlaps the kernels of the previous one)")
+    ap.add_argument("--e2e-tiles", type=int, default=13, help="time tiles per e2e step (H2D of a tile overlaps the kernels of the previous one; 13 = one-frame tiles: the shorter the last tile, the less kernel time trails the last copy)")
     ap.add_argument("--e2e-ring-tiles", type=int, default=2, help="device ring of the e2e leg, in tiles (+ one frame of carry)")
     ap.add_argument("--bank-streams", type=int, default=0,
                     help="streams per GPU of the channel-bank leg (0 = 4 CTAs x 32 streams per SM, 18,944 on a B200)")

@@ -2,7 +2,7 @@
 # Round 2, call X: e2e leg against the number of time tiles and the ring depth, and the copy-only rate of the same pushes.
 set -x -o pipefail
 mkdir -p gpurun_out
-for CFG in "8 2" "8 3" "8 4" "16 4"; do set -- $CFG
+for CFG in "8 2" "12 2" "16 2" "24 2"; do set -- $CFG
   timeout 200 python bench.py --steps 3 --warmup 3 --no-bank --no-cpu-baseline --e2e-tiles $1 --e2e-ring-tiles $2 2>gpurun_out/x.err | tail -1 > gpurun_out/x_$1_$2.json
   python -c "
 import json
