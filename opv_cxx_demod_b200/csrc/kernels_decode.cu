@@ -270,6 +270,8 @@ void launch_decode(const SoftBuffers& so, const FrameTask* tasks, const int32_t*
     if (n_tasks_host <= 0) return;
     const size_t smem = (size_t)kBmTableBytes + (size_t)kDecWarps * kDecSmemPerWarp;
     cudaFuncSetAttribute(decode_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device
+    prefer_max_shared(decode_tasks_kernel);
+    prefer_max_shared(log_advance_kernel);
     decode_tasks_kernel<<<decode_grid(n_tasks_host), 32 * kDecWarps, smem, st>>>(so, tasks, n_tasks_dev, n_tasks_host,
                                                                               frames, metrics, max_frames, frec, log,
                                                                               log_count, log_cap, counters);
@@ -281,6 +283,7 @@ void launch_decode_payloads(const double* payloads, int n, uint8_t* frames, int3
     if (n <= 0) return;
     const size_t smem = (size_t)kBmTableBytes + (size_t)kDecWarps * kDecSmemPerWarp;
     cudaFuncSetAttribute(decode_payloads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device
+    prefer_max_shared(decode_payloads_kernel);
     decode_payloads_kernel<<<decode_grid(n), 32 * kDecWarps, smem, st>>>(payloads, n, frames, metrics, counters);
 }
 

@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(kEstThreads) est_kernel(StreamBuffers sb, Demo
 void launch_estimate(const StreamBuffers& sb, DemodState* dstate, double* est_out, int n_streams, int mode,
                      int final_flag, cudaStream_t st) {
     if (n_streams <= 0) return;
+    prefer_max_shared(est_kernel);
     est_kernel<<<n_streams, kEstThreads, 0, st>>>(sb, dstate, est_out, n_streams, mode, final_flag);
 }
 

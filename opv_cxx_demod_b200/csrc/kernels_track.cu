@@ -151,6 +151,7 @@ void launch_track(const SoftBuffers& so, TrackState* tstate, int n_streams,
                   cudaStream_t st) {
     if (n_streams <= 0) return;
     const int grid = (n_streams + kTrackWarps - 1) / kTrackWarps;
+    prefer_max_shared(track_kernel);
     track_kernel<<<grid, 32 * kTrackWarps, 0, st>>>(so, tstate, n_streams, frec, max_frames, events,
                                                     n_events, max_events, tasks, n_tasks, max_tasks, counters);
 }

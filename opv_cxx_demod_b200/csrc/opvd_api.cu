@@ -488,6 +488,7 @@ int opvd_run(opvd_handle* h, int final_flag) {
     int64_t* snap = h->h_snap + (size_t)slot * h->S;
     std::copy(h->h_avail.begin(), h->h_avail.end(), snap);
     int64_t* d_avail = h->d_avail + (size_t)slot * h->S;
+    prefer_max_shared(snapshot_kernel);
     snapshot_kernel<<<(h->S + 255) / 256, 256, 0, h->st>>>(d_avail, h->h_snap_dev + (size_t)slot * h->S, h->S);
     if (h->copy_pending) {  // pushed samples must have landed before the kernels read them (device-side wait)
         CK(cudaStreamWaitEvent(h->st, h->ev_copy, 0));
@@ -580,17 +581,18 @@ int opvd_poll_frames(opvd_handle* h, int32_t max_frames, uint8_t* frames134, opv
     if (!h->d_log) return 0;
     // ---- fetch what the runs enqueued so far have logged since the last poll
     if (h->run_seq > 0) CK(cudaEventSynchronize(h->ev_back[(h->run_seq - 1) % kRuns]));
-    if (h->trace && h->tr_n > 0 && h->run_seq > 0 && h->run_seq <= kRuns) {
+    if (h->trace && h->run_seq > 0 && h->run_seq <= kRuns) {
         CK(cudaStreamSynchronize(h->st_copy));
         float a = 0.f, b = 0.f;
+        const cudaEvent_t base = h->tr_n > 0 ? h->tr_c0[0] : h->ev_t[0][0];
         for (int i = 0; i < h->tr_n; ++i) {
-            cudaEventElapsedTime(&a, h->tr_c0[0], h->tr_c0[i]);
-            cudaEventElapsedTime(&b, h->tr_c0[0], h->tr_c1[i]);
+            cudaEventElapsedTime(&a, base, h->tr_c0[i]);
+            cudaEventElapsedTime(&b, base, h->tr_c1[i]);
             fprintf(stderr, "opvd trace: push %d copy %.2f .. %.2f ms\n", i, a, b);
         }
         for (long long r = 0; r < h->run_seq; ++r) {
             float t[5];
-            for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], h->tr_c0[0], h->ev_t[r % kRuns][i]);
+            for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], base, h->ev_t[r % kRuns][i]);
             fprintf(stderr, "opvd trace: run %lld front %.2f est %.2f demod %.2f | back track %.2f decode %.2f ms\n", r, t[0], t[1], t[2], t[3], t[4]);
         }
         h->tr_n = 0;

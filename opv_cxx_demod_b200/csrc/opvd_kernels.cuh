@@ -108,6 +108,15 @@ void launch_estimate(const StreamBuffers& sb, DemodState* dstate, double* est_ou
 
 // lanes_per_stream in {32, 96}; 0 = chosen from the stream count (demod_select.cu); returns cudaError
 //   32   warp per stream (kernels_demod_warp.cu)      96   channel bank, three role warps per 32 streams
+// Every kernel of the chain asks for the same (largest) shared-memory carveout: an SM can only change its L1/shared
+// split while it is empty, so a kernel with a different preference cannot join CTAs that are already resident - the
+// tracker and the Viterbi decoder of tile t then wait for the demodulator of tile t+1 to drain instead of running
+// beside it (measured with OPVD_TRACE: every second decode launch took a whole tile).
+template <class Kernel>
+inline void prefer_max_shared(Kernel kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+
 cudaError_t launch_demod(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                          int mode, int final_flag, double afc_alpha, int lanes_per_stream,
                          unsigned long long* counters, cudaStream_t st);

@@ -39,6 +39,8 @@ for rep in range(a.reps):
             bank.attach_device_iq(buf.data_ptr(), stride, avail, keepalive=buf)
             bank.run(final=(t == a.tiles - 1), sync=False)
     ms = bank.last_run_ms(); c = bank.counters()
+    if os.environ.get("OPVD_TRACE"):
+        bank.poll_frames()  # prints the timeline of the runs (at most 8)
     t1 = time.time()
     tot = ms["total"] / 1e3
     print(json.dumps({"rep": rep, "S": S, "frames": nf, "ms": ms, "wall_s": round(t1 - t0, 4),
