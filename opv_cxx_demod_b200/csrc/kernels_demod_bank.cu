@@ -37,8 +37,10 @@ constexpr int kChunk = 8;            // samples per 32-byte sector
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kQBias = 0x80000000u;
 
-// named barriers (0 is __syncthreads)
-enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3 };
+// named barriers.  The two CTA-wide rendezvous (after set-up, before exit) are reached from three different role
+// functions, so they are a counted named barrier (kBarCta, 96 threads) rather than __syncthreads(), whose contract asks
+// every thread to reach the SAME call site.
+enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3, kBarCta = 4 };
 enum : int { kFlagTone1 = 1, kFlagFirst = 2, kFlagLive = 4, kFlagExit = 8 };
 
 // RING = samples per stream resident in shared memory (a multiple of 8).  The ring is what limits the number of
@@ -252,7 +254,7 @@ __device__ __forceinline__ void role_afc(SM& sm, int s, int stream, bool valid, 
         bank_lo_from_zeta(zeta, d, lo, g_fm);
         bank_pow_from_zeta(zeta, pw, g_bk);
     }
-    __syncthreads();  // (1)
+    bar_sync<kBarCta, 96>();  // (1)
     auto publish_z = [&]() {
         sm.z[0][s] = lo.z1.r; sm.z[1][s] = lo.z1.i; sm.z[2][s] = lo.z2.r; sm.z[3][s] = lo.z2.i;
         bar_arrive<kBarZ, NW>();
@@ -286,7 +288,7 @@ __device__ __forceinline__ void role_afc(SM& sm, int s, int stream, bool valid, 
         if (update) bank_pow_from_zeta(zeta, pw, g_bk);
         publish_pow();
     }
-    __syncthreads();  // (2) the window warp has written the records
+    bar_sync<kBarCta, 96>();  // (2) the window warp has written the records
     if (valid) {
         DemodState* d = dstate + stream;
         d->freq_offset = afc.freq_offset; d->ph1 = afc.ph1; d->ph2 = afc.ph2; d->p1 = afc.p1; d->p2 = afc.p2;
@@ -304,7 +306,7 @@ __device__ __forceinline__ void role_stage(SM& sm, int s, int stream, const Stre
     const RowView view = make_row_view(sb, stream, dstate[stream].origin);  // same base as the window warp
     const bool wide = ((reinterpret_cast<uintptr_t>(sb.iq) | (uintptr_t)(sb.stride * 4)) & 31u) == 0;
     sm.fill[s] = -(1 << 30);
-    __syncthreads();  // (1)
+    bar_sync<kBarCta, 96>();  // (1)
     int req;  // samples [.., req) of this lane's row have been requested (multiple of 8)
     {
         const int w0 = sm.w0[s];
@@ -342,7 +344,7 @@ __device__ __forceinline__ void role_stage(SM& sm, int s, int stream, const Stre
         if (ld_vol(&sm.exit_flag)) break;
         __nanosleep(700);
     }
-    __syncthreads();  // (2)
+    bar_sync<kBarCta, 96>();  // (2)
 }
 
 }  // namespace
@@ -372,7 +374,7 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     sm.w0[s] = c.w0;
     sm.live[s] = c.live ? 1 : 0;
     if (s == 0) sm.exit_flag = 0;
-    __syncthreads();  // (1) symbol 0 published
+    bar_sync<kBarCta, 96>();  // (1) symbol 0 published
     bool any_live = __any_sync(kFull, c.live);
     while (any_live) {
         const bool first = c.sym_in_call == 0;
@@ -410,7 +412,7 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     st_vol(&sm.exit_flag, 1);
     bar_arrive<kBarO, 64>();  // the AFC warp waits for the next on-time correlations
     if (valid) c.persist(st, so, dstate, stream, counters);
-    __syncthreads();  // (2)
+    bar_sync<kBarCta, 96>();  // (2)
 }
 
 template <int QX, int RING, int MINB>
