@@ -21,6 +21,8 @@ namespace opvd {
 // Integer accumulation (one IMAD.WIDE s32 x s32 + s64 per product instead of one DFMA) was measured in round 2 and is
 // slower on B200: 12.0 ms against 8.4 ms for 18,944 streams.  The 64-bit integer multiply-add issues at a lower rate
 // than the FP64 pipe's DFMA.
+// Double-buffered staging (one CTA barrier per pass, the next pass fetched into registers before the products of this
+// one) was measured too: 8.24 ms against 8.37 ms, at 96 instead of 66 registers and twice the shared memory - not kept.
 constexpr int kEstSlots = 32;                 // blocks per pass
 constexpr int kEstRoles = 5;
 constexpr int kEstThreads = kEstSlots * kEstRoles;   // 160
