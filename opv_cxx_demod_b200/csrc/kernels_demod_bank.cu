@@ -40,18 +40,20 @@ constexpr uint32_t kQBias = 0x80000000u;
 // named barriers.  The two CTA-wide rendezvous (after set-up, before exit) are reached from three different role
 // functions, so they are a counted named barrier (kBarCta, 96 threads) rather than __syncthreads(), whose contract asks
 // every thread to reach the SAME call site.
-enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3, kBarCta = 4 };
+enum : int { kBarO = 1, kBarZ = 2, kBarPow = 3, kBarCta = 4, kBarWin = 5, kBarEl = 6 };
 enum : int { kFlagTone1 = 1, kFlagFirst = 2, kFlagLive = 4, kFlagExit = 8 };
 
 // RING = samples per stream resident in shared memory (a multiple of 8).  The ring is what limits the number of
 // resident CTAs per SM: 256 rows -> 45.0 KB -> 4 CTAs, 240 -> 5, 176 -> 6, 144 -> 7.
-template <int RING>
+template <int RING, bool ELB = false>
 struct __align__(16) BankSmem {
     static constexpr int kRingRows = RING;
+    static constexpr bool kElb = ELB;
     uint32_t ring[RING + kMirrorRows][kSpc];
     double o[4][kSpc];            // WINDOW -> AFC: O1.r, O1.i, O2.r, O2.i
     double z[4][kSpc];            // AFC -> WINDOW: z1.r, z1.i, z2.r, z2.i
     double pw[10][kSpc];          // AFC -> WINDOW: q1, q2, qq1, qq2, zeta40
+    double el[ELB ? 12 : 1][kSpc];  // AFC -> WINDOW (ELB): H0 (F1), H0 (F2), H5 (F1), H5 (F2), s0, s60
     int flags[kSpc];              // WINDOW -> AFC: kFlag*
     int w0[kSpc];                 // WINDOW -> STAGE: row-relative sample index of window slot 0 of the current symbol
     int fill[kSpc];               // STAGE -> WINDOW: samples [.., fill) of the stream's row are in the ring
@@ -242,7 +244,9 @@ __device__ __forceinline__ void load_pow(const SM& sm, int s, BankPow& pw) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // AFC role.  NW = threads taking part in the z / power hand-offs (64: one window warp, 96: two).
-template <int NW, class SM>
+// ELB: this warp also evaluates the early / late block sums H0, H5 of both tones (bank_el_blocks) while the window warp
+// works on the on-time blocks; it is woken by kBarWin when the window of the symbol has been published.
+template <int NW, int QX, class SM>
 __device__ __forceinline__ void role_afc(SM& sm, int s, int stream, bool valid, DemodState* dstate, double afc_alpha) {
     const DemodState* d0 = dstate + stream;
     BankAfc afc = {d0->freq_offset, d0->ph1, d0->ph2, d0->p1, d0->p2};
@@ -268,6 +272,20 @@ __device__ __forceinline__ void role_afc(SM& sm, int s, int stream, bool valid, 
     publish_z();
     publish_pow();
     for (;;) {
+        if (SM::kElb) {
+            bar_sync<kBarWin, 64>();  // the window of this symbol is published (or the launch is over)
+            if (ld_vol(&sm.exit_flag)) break;
+            const int w0 = ld_vol(&sm.w0[s]);
+            wait_window(sm, s, ld_vol(&sm.live[s]) != 0, w0);
+            const uint32_t* const win = &sm.ring[ring_row<SM::kRingRows>(w0)][s];
+            auto slot = [&](int k, double& I, double& Q) { unpack_ring<QX>(win[k * kSpc], k, I, Q); };
+            BankElBlocks e;
+            bank_el_blocks(slot, lo.z1, lo.z2, e);
+            sm.el[0][s] = e.H0a.r; sm.el[1][s] = e.H0a.i; sm.el[2][s] = e.H0b.r; sm.el[3][s] = e.H0b.i;
+            sm.el[4][s] = e.H5a.r; sm.el[5][s] = e.H5a.i; sm.el[6][s] = e.H5b.r; sm.el[7][s] = e.H5b.i;
+            sm.el[8][s] = e.s0.r; sm.el[9][s] = e.s0.i; sm.el[10][s] = e.s60.r; sm.el[11][s] = e.s60.i;
+            bar_arrive<kBarEl, 64>();
+        }
         bar_sync<kBarO, 64>();
         const int fl = sm.flags[s];
         if (fl & kFlagExit) break;  // warp-uniform: the window warp sets it on every lane
@@ -353,19 +371,19 @@ __device__ __forceinline__ void role_stage(SM& sm, int s, int stream, const Stre
 // Three-warp kernel: WINDOW, AFC, STAGE (96 threads)
 // RING / MINB: ring rows per stream and the resident CTAs per SM they allow.  The register cap is written out
 // (65,536 / (96 MINB) rounded down to the allocation unit of 8): __launch_bounds__' own choice is more conservative.
-template <int QX, int RING, int MINB>
+template <int QX, int RING, int MINB, bool ELB>
 __global__ void __maxnreg__(MINB == 4 ? 168 : MINB == 5 ? 136 : MINB == 6 ? 112 : 96)
 demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
                   int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using SM = BankSmem<RING>;
+    using SM = BankSmem<RING, ELB>;
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
     const int s = threadIdx.x & 31, role = threadIdx.x >> 5;
     const int stream_raw = blockIdx.x * kSpc + s;
     const bool valid = stream_raw < n_streams;
     const int stream = valid ? stream_raw : n_streams - 1;
 
-    if (role == 1) { role_afc<64>(sm, s, stream, valid, dstate, afc_alpha); return; }
+    if (role == 1) { role_afc<64, QX>(sm, s, stream, valid, dstate, afc_alpha); return; }
     if (role == 2) { role_stage<QX, (RING >= 176 ? 5 : 3)>(sm, s, stream, sb, dstate); return; }
 
     DemodState st = dstate[stream];  // local memory: only the scheduler touches it
@@ -378,6 +396,7 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     bool any_live = __any_sync(kFull, c.live);
     while (any_live) {
         const bool first = c.sym_in_call == 0;
+        if (ELB) bar_arrive<kBarWin, 64>();  // the AFC warp may start on the early / late blocks of this window
         bar_sync<kBarZ, 64>();
         BankLo lo;
         load_lo(sm, s, lo);
@@ -399,7 +418,15 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
         cplx fixE = {0.0, 0.0};
         if (first && c.live) fixE = first_fix_cold<QX>(win, c.f, tone1 ? lo.z1 : lo.z2);  // :237, once per call
         double eE, eL;
-        bank_early_late(slot, c.f, tone1, lo, pw, on, fixE, eE, eL);
+        if (ELB) {
+            bar_sync<kBarEl, 64>();  // block sums H0, H5 of both tones from the AFC warp
+            const int t = tone1 ? 0 : 2;
+            const cplx H0 = {sm.el[t][s], sm.el[t + 1][s]}, H5 = {sm.el[4 + t][s], sm.el[5 + t][s]};
+            const cplx s0 = {sm.el[8][s], sm.el[9][s]}, s60 = {sm.el[10][s], sm.el[11][s]};
+            bank_early_late_from_blocks(c.f, tone1, lo, pw, on, H0, H5, s0, s60, fixE, eE, eL);
+        } else {
+            bank_early_late(slot, c.f, tone1, lo, pw, on, fixE, eE, eL);
+        }
         if (c.live) {
             bank_timing(eE, eL, c.timing_freq, c.pos, g_fm);
             c.advance(st, mode, final_flag);
@@ -410,23 +437,24 @@ demod_bank_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dst
     }
     sm.flags[s] = kFlagExit;
     st_vol(&sm.exit_flag, 1);
-    bar_arrive<kBarO, 64>();  // the AFC warp waits for the next on-time correlations
+    if (ELB) bar_arrive<kBarWin, 64>();  // the AFC warp waits for the next window
+    else bar_arrive<kBarO, 64>();        // ... or for the next on-time correlations
     if (valid) c.persist(st, so, dstate, stream, counters);
     bar_sync<kBarCta, 96>();  // (2)
 }
 
-template <int QX, int RING, int MINB>
+template <int QX, int RING, int MINB, bool ELB>
 static cudaError_t launch_bank_t(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams, int mode,
                                  int final_flag, double afc_alpha, unsigned long long* counters, cudaStream_t st) {
-    const size_t smem = sizeof(BankSmem<RING>);
-    cudaError_t e = cudaFuncSetAttribute(demod_bank_kernel<QX, RING, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = sizeof(BankSmem<RING, ELB>);
+    cudaError_t e = cudaFuncSetAttribute(demod_bank_kernel<QX, RING, MINB, ELB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // all of the SM's shared memory, or the resident CTAs the ring was sized for do not fit
-    e = cudaFuncSetAttribute(demod_bank_kernel<QX, RING, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(demod_bank_kernel<QX, RING, MINB, ELB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     const int grid = (n_streams + kSpc - 1) / kSpc;
-    demod_bank_kernel<QX, RING, MINB><<<grid, 96, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
+    demod_bank_kernel<QX, RING, MINB, ELB><<<grid, 96, smem, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
     return cudaGetLastError();
 }
 // Measured and dropped: more resident CTAs per SM through smaller rings and register caps
@@ -435,7 +463,14 @@ static cudaError_t launch_bank_t(const StreamBuffers& sb, const SoftBuffers& so,
 cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, DemodState* dstate, int n_streams,
                               int mode, int final_flag, double afc_alpha, unsigned long long* counters,
                               cudaStream_t st) {
-    return launch_bank_t<1, 256, 4>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    // ELB (the AFC warp takes the early / late block sums) pays while SM sub-partitions are idle: up to one CTA per SM
+    // (probe banks x 6 frames: 4,736 streams 14.4 against 15.9 ms; 9,472 streams 18.7 against 16.9 ms)
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static const int force = getenv("OPVD_BANK_ELB") ? atoi(getenv("OPVD_BANK_ELB")) : -1;  // development switch
+    const bool elb = force >= 0 ? force != 0 : (n_streams + kSpc - 1) / kSpc <= sms;
+    if (elb) return launch_bank_t<1, 256, 4, true>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    return launch_bank_t<1, 256, 4, false>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
 }
 
 }  // namespace opvd

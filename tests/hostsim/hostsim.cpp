@@ -165,8 +165,8 @@ size_t hostsim_demod_warp(const int16_t* iq, size_t n, int mode, double afc_alph
 
 // whole stream through the CHANNEL-BANK decomposition (demod_bank_core.cuh, kernels_demod_bank.cu): on-time sums of
 // both tones, early/late sums of the dominant tone only, LO powers from one zeta chain.  Same contract as hostsim_demod.
-size_t hostsim_demod_bank(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
-                          double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
+static size_t demod_bank_impl(bool elb, const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
+                              double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
     std::vector<uint32_t> w(n + 64 + 64, 0xDEADBEEFu);
     for (size_t i = 0; i < n; ++i)
         w[64 + i] = (uint32_t)(uint16_t)iq[2 * i] | ((uint32_t)(uint16_t)iq[2 * i + 1] << 16);
@@ -211,7 +211,14 @@ size_t hostsim_demod_bank(const int16_t* iq, size_t n, int mode, double afc_alph
         cplx fixE = {0.0, 0.0};
         if (first) fixE = first_symbol_fix(win, f, tone1 ? lo.z1 : lo.z2);
         double eE, eL;
-        bank_early_late(slot, f, tone1, lo, pw, on, fixE, eE, eL);
+        if (elb) {  // the AFC warp evaluates H0, H5 of both tones, the window warp combines the dominant tone's
+            BankElBlocks e;
+            bank_el_blocks(slot, lo.z1, lo.z2, e);
+            bank_early_late_from_blocks(f, tone1, lo, pw, on, tone1 ? e.H0a : e.H0b, tone1 ? e.H5a : e.H5b, e.s0, e.s60, fixE,
+                                        eE, eL);
+        } else {
+            bank_early_late(slot, f, tone1, lo, pw, on, fixE, eE, eL);
+        }
         bank_timing(eE, eL, timing_freq, pos, g_fm);
         // AFC role
         bank_afc(afc, on.O1, on.O2, tone1, pw.zeta40, lo.inc1, lo.inc2, first, afc_alpha, g_fm);
@@ -232,6 +239,16 @@ size_t hostsim_demod_bank(const int16_t* iq, size_t n, int mode, double afc_alph
     return ns;
 }
 
+
+size_t hostsim_demod_bank(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
+                          double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
+    return demod_bank_impl(false, iq, n, mode, afc_alpha, have_init, init_offset, soft_out, cap, est_out, final_freq, final_tfreq);
+}
+// the same with the early / late block sums taken by the AFC role (the kernel's choice for banks of up to one CTA per SM)
+size_t hostsim_demod_bank_elb(const int16_t* iq, size_t n, int mode, double afc_alpha, int have_init, double init_offset,
+                              double* soft_out, size_t cap, double* est_out, double* final_freq, double* final_tfreq) {
+    return demod_bank_impl(true, iq, n, mode, afc_alpha, have_init, init_offset, soft_out, cap, est_out, final_freq, final_tfreq);
+}
 
 // coherent mode (-c, batch only) through demod_coherent_core.cuh.  Returns number of soft symbols.
 size_t hostsim_demod_coherent(const int16_t* iq, size_t n, double afc_alpha, double pll_bw, double* soft_out, size_t cap,

@@ -31,6 +31,8 @@ def sim():
     H.hostsim_demod_warp.argtypes = H.hostsim_demod.argtypes
     H.hostsim_demod_bank.restype = C.c_size_t
     H.hostsim_demod_bank.argtypes = H.hostsim_demod.argtypes
+    H.hostsim_demod_bank_elb.restype = C.c_size_t
+    H.hostsim_demod_bank_elb.argtypes = H.hostsim_demod.argtypes
     H.hostsim_demod_coherent.restype = C.c_size_t
     H.hostsim_demod_coherent.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_void_p, C.c_size_t,
                                          C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -46,7 +48,7 @@ NAMES = ["clean5", "clean12_call", "awgn14", "awgn8", "awgn4", "cfo_p1200_delay"
 
 @pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("variant", ["lane", "warp", "bank"])
+@pytest.mark.parametrize("variant", ["lane", "warp", "bank", "bank_elb"])
 def test_device_arithmetic_vs_oracle(name, mode, variant, cases, ora, sim):
     iq = cases[name]
     a = np.ascontiguousarray(iq, np.int16).reshape(-1)
@@ -54,7 +56,7 @@ def test_device_arithmetic_vs_oracle(name, mode, variant, cases, ora, sim):
     ref = ora.run(iq, bool(mode))
     soft = np.zeros(n // 40 + 16)
     est, ff, tf = C.c_double(), C.c_double(), C.c_double()
-    fn = {"lane": sim.hostsim_demod, "warp": sim.hostsim_demod_warp, "bank": sim.hostsim_demod_bank}[variant]
+    fn = {"lane": sim.hostsim_demod, "warp": sim.hostsim_demod_warp, "bank": sim.hostsim_demod_bank, "bank_elb": sim.hostsim_demod_bank_elb}[variant]
     ns = fn(a.ctypes.data, n, mode, 0.001, 0, 0.0, soft.ctypes.data, soft.size, C.byref(est),
                            C.byref(ff), C.byref(tf))
     soft = soft[:ns]
