@@ -12,11 +12,12 @@
 namespace opvd {
 
 int demod_auto_lanes(int n_streams) {
-    // Measured crossover (profiles/gpu_r02_f.log): the bank kernel needs 2.38 ms per frame for anything up to one CTA
-    // per SM (4,736 streams); the warp-per-stream kernel 1.41 ms per frame at 1,024 streams and 2.59 ms at 1,280.
+    // Measured crossover (profiles/gpu_r02_wb.log, gpu_r02_elb.log, 12-frame banks): the warp-per-stream kernel holds 8
+    // CTAs per SM in its fast build (1,184 streams, 16.2 ms at 1,024) and 16 in its 124-register build (23.3 ms at 1,536,
+    // 29.7 ms at 2,048); the bank kernel needs 28.5 ms for anything up to one CTA per SM (4,736 streams).
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if ((long long)n_streams <= 8ll * sms) return 32;
+    if ((long long)n_streams <= 12ll * sms) return 32;
     return 96;
 }
 

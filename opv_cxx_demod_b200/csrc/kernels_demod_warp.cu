@@ -186,7 +186,11 @@ struct WarpCtx {
 
 }  // namespace
 
-__global__ void __launch_bounds__(32)
+// MINB: resident CTAs per SM the register budget is cut for.  8 (188 registers) is what ptxas takes unconstrained;
+// 16 (124 registers, still no spill, 12 % more time per symbol) doubles the streams that fit in one wave, from 1,184
+// to 2,368 on a B200: banks just beyond one wave of the fast build would otherwise take two.
+template <int MINB>
+__global__ void __launch_bounds__(32, MINB)
 demod_warp_kernel(StreamBuffers sb, SoftBuffers so, DemodState* __restrict__ dstate, int n_streams, int mode,
                   int final_flag, double afc_alpha, unsigned long long* __restrict__ counters) {
     __shared__ __align__(128) uint32_t ring_sm[kRingWords];
@@ -277,8 +281,15 @@ cudaError_t launch_demod_warp(const StreamBuffers& sb, const SoftBuffers& so, De
     // SM only changes while the SM is empty, and with a small carveout the tracker/decoder CTAs of the previous time
     // tile (22 KB each, second CUDA stream) could not be placed beside the resident demodulator CTAs: they ran after
     // them instead of with them.  The kernel streams its samples through cp.async.cg (L2 only), so it loses nothing.
-    cudaFuncSetAttribute(demod_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    demod_warp_kernel<<<n_streams, 32, 0, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (n_streams > 8 * sms) {  // more streams than one wave of the 188-register build
+        prefer_max_shared(demod_warp_kernel<16>);
+        demod_warp_kernel<16><<<n_streams, 32, 0, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
+    } else {
+        prefer_max_shared(demod_warp_kernel<8>);
+        demod_warp_kernel<8><<<n_streams, 32, 0, st>>>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters);
+    }
     return cudaGetLastError();
 }
 

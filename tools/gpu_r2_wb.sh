@@ -1,15 +1,10 @@
 #!/bin/bash
-# Round 2: the warp kernel cut for 16 resident CTAs per SM (124 registers) against the 182-register build and the bank kernel.
+# Round 2: automatic kernel choice across the crossover (warp kernel 188 / 124 registers, bank kernel with / without ELB).
 set -x -o pipefail
 mkdir -p gpurun_out
 P="timeout 90 python tools/probe.py --frames 12 --reps 2"
-OPVD_WARP_MINB=8  $P --streams 1024 --lanes 32 2>&1 | tail -1 | cut -c1-200 || exit 1
-OPVD_WARP_MINB=16 $P --streams 1024 --lanes 32 2>&1 | tail -1 | cut -c1-200
-for S in 1536 2048 2368; do
-  OPVD_WARP_MINB=16 $P --streams $S --lanes 32 2>&1 | tail -1 | cut -c1-200
-  $P --streams $S --lanes 96 2>&1 | tail -1 | cut -c1-200
+for S in 1024 1184 1500 1776 1800 2368 4736; do
+  $P --streams $S 2>&1 | tail -1 | python -c "
+import sys, json; d = json.loads(sys.stdin.read()); print('S', d['S'], 'auto demod', round(d['ms']['demod'], 3))" || exit 1
 done
-for S in 3072 4096; do
-  OPVD_WARP_MINB=16 $P --streams $S --lanes 32 2>&1 | tail -1 | cut -c1-200
-  $P --streams $S --lanes 96 2>&1 | tail -1 | cut -c1-200
-done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
