@@ -73,7 +73,8 @@ __device__ __forceinline__ void st_vol(int* p, int v) { *reinterpret_cast<volati
 //   QX = 0  Q stored offset-binary; 2^52 bias trick (two integer-pipe instructions + one DADD on the FP64 pipe)
 //   QX = 1  Q stored offset-binary; odd window slots through XU (after undoing the offset), even slots bias trick
 //   QX = 2  Q stored raw; one I2F.F64.S16 on the upper half (every conversion on the XU pipe)
-// The kernel is bound by issue slots, the FP64 pipe and the XU pipe at nearly the same level; QX balances them.
+// The kernel is bound by issue slots, the FP64 pipe and the XU pipe at nearly the same level; QX balances them (the
+// launcher's default is QX = 0, 1 % ahead of the others on the full bank; no difference on the ELB path).
 template <int QX>
 __device__ __forceinline__ void unpack_ring(uint32_t w, int k, double& I, double& Q) {
     I = (double)(int16_t)(w & 0xFFFFu);
@@ -469,8 +470,13 @@ cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, De
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     static const int force = getenv("OPVD_BANK_ELB") ? atoi(getenv("OPVD_BANK_ELB")) : -1;  // development switch
     const bool elb = force >= 0 ? force != 0 : (n_streams + kSpc - 1) / kSpc <= sms;
-    if (elb) return launch_bank_t<1, 256, 4, true>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
-    return launch_bank_t<1, 256, 4, false>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    // Q conversion split (unpack_ring): every split gives the same values; on the full bank QX = 0 measured 19.84 ms,
+    // QX = 1 20.03 ms, QX = 2 20.24 ms (profiles/gpu_r02_qx.log).  OPVD_BANK_QX: development switch.
+    static const int qx = getenv("OPVD_BANK_QX") ? atoi(getenv("OPVD_BANK_QX")) : 0;
+    if (elb) return launch_bank_t<0, 256, 4, true>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    if (qx == 1) return launch_bank_t<1, 256, 4, false>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    if (qx == 2) return launch_bank_t<2, 256, 4, false>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
+    return launch_bank_t<0, 256, 4, false>(sb, so, dstate, n_streams, mode, final_flag, afc_alpha, counters, st);
 }
 
 }  // namespace opvd
