@@ -313,10 +313,10 @@ def run_bank_leg(args, pkg, torch, dev, local_rank, world, S, first_stream, n_fr
                                    "frac": round(dfma / mb["dfma_per_s"], 4),
                                    "note": "12 DFMA per sample is the Horner correlator's algorithmic count for six full "
                                            "gates; the kernel evaluates early/late gates for the dominant tone only"}
-        # the honest bar: this kernel executes 15.5 FP64-pipe instructions per sample (profiles/sass_bank_r02.txt), so
+        # the honest bar: this kernel executes 16.4 FP64-pipe instructions per sample (profiles/sass_bank_r02.txt), so
         # the FP64 pipe, not HBM, is its lower ceiling: min(HBM, FP64) in bytes per second
-        fp64_ceiling = mb["dfma_per_s"] / 15.5 * 4 / 1e9
-        out["roofline"]["min_hbm_fp64"] = {"fp64_instr_per_sample": 15.5, "fp64_ceiling_gbs": round(fp64_ceiling, 1),
+        fp64_ceiling = mb["dfma_per_s"] / 16.4 * 4 / 1e9
+        out["roofline"]["min_hbm_fp64"] = {"fp64_instr_per_sample": 16.4, "fp64_ceiling_gbs": round(fp64_ceiling, 1),
                                            "ceiling_gbs": round(min(peak, fp64_ceiling), 1),
                                            "frac": round(ach / min(peak, fp64_ceiling), 4),
                                            "note": "FP64 issue ceiling at the measured 2.2 cycles per DFMA; with the three-register "
