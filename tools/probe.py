@@ -12,11 +12,12 @@ ap.add_argument("--lanes", type=int, default=0)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--tiles", type=int, default=1, help="time tiles per pass (attach a growing prefix, run each)")
 ap.add_argument("--tile-frames", default="", help="comma-separated frame counts at which the time tiles end (overrides --tiles)")
+ap.add_argument("--stride-frames", type=int, default=0, help="row pitch as if the captures were this many frames long (address span without more data)")
 ap.add_argument("--ebn0", type=float, nargs=2, default=[2.0, 10.0])
 a = ap.parse_args()
 S, nf = a.streams, a.frames
 n = nf * 86720 + 8000
-stride = (n + 63) // 64 * 64
+stride = (max(n, a.stride_frames * 86720 + 8000) + 63) // 64 * 64
 buf = torch.empty((S, stride), dtype=torch.int32, device="cuda")
 sp = pkg.make_synth(S, nf, stride, n, seed=1, ebn0_lo_db=a.ebn0[0], ebn0_hi_db=a.ebn0[1], cfo_max_hz=0.0, max_lead=4000)
 t0 = time.time(); pkg.synth_bank(buf.data_ptr(), sp); torch.cuda.synchronize(); t1 = time.time()
