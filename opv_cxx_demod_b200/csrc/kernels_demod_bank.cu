@@ -37,6 +37,9 @@ constexpr int kChunk = 8;            // samples per 32-byte sector
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kQBias = 0x80000000u;
 
+__device__ unsigned g_stage_sleep_ns = 400;  // pacing of the STAGE warp; flat between 300 and 1,000 ns (19.85 .. 20.0 ms on the full
+                                              // probe bank, profiles/gpu_r02_sleep.log).  OPVD_BANK_SLEEP: development switch
+
 // named barriers.  The two CTA-wide rendezvous (after set-up, before exit) are reached from three different role
 // functions, so they are a counted named barrier (kBarCta, 96 threads) rather than __syncthreads(), whose contract asks
 // every thread to reach the SAME call site.
@@ -339,7 +342,7 @@ __device__ __forceinline__ void role_stage(SM& sm, int s, int stream, const Stre
     // kernel on a shared box costs more than the ~25 polling instructions per symbol this loop spends.  The first version
     // polled every 200 ns with a heavy loop body and spent ~670 instructions per symbol, on a sub-partition it shares
     // with another CTA's window warp.)  Steady state per round: store the batch requested before the last sleep (its
-    // loads have had ~0.7 us to land), request the next one, sleep.  A stream that is close to starving (start of a
+    // loads have had a sleep and a round to land), request the next one, sleep.  A stream that is close to starving (start of a
     // launch, end of a row, catching up after a stall) is served without sleeping.
     for (;;) {
         const int w0 = ld_vol(&sm.w0[s]);
@@ -361,7 +364,7 @@ __device__ __forceinline__ void role_stage(SM& sm, int s, int stream, const Stre
         const bool urgent = idx >= 0 && pub < w0 + kUrgent;  // the window may need this batch before the next round
         if (__any_sync(kFull, urgent)) continue;
         if (ld_vol(&sm.exit_flag)) break;
-        __nanosleep(700);
+        __nanosleep(g_stage_sleep_ns);
     }
     bar_sync<kBarCta, 96>();  // (2)
 }
@@ -470,6 +473,11 @@ cudaError_t launch_demod_bank(const StreamBuffers& sb, const SoftBuffers& so, De
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     static const int force = getenv("OPVD_BANK_ELB") ? atoi(getenv("OPVD_BANK_ELB")) : -1;  // development switch
     const bool elb = force >= 0 ? force != 0 : (n_streams + kSpc - 1) / kSpc <= sms;
+    static const int sleep_ns = getenv("OPVD_BANK_SLEEP") ? atoi(getenv("OPVD_BANK_SLEEP")) : 0;
+    if (sleep_ns > 0) {
+        const unsigned v = (unsigned)sleep_ns;
+        cudaMemcpyToSymbolAsync(g_stage_sleep_ns, &v, sizeof(v), 0, cudaMemcpyHostToDevice, st);
+    }
     // Q conversion split (unpack_ring): every split gives the same values; on the full bank QX = 0 measured 19.84 ms,
     // QX = 1 20.03 ms, QX = 2 20.24 ms (profiles/gpu_r02_qx.log).  OPVD_BANK_QX: development switch.
     static const int qx = getenv("OPVD_BANK_QX") ? atoi(getenv("OPVD_BANK_QX")) : 0;
