@@ -356,7 +356,7 @@ def run_sustained(args, pkg, torch, np, dev, local_rank, world, S, bank_buf, bar
             sbank.push_iq_host_ptr(host.data_ptr(), FRAME_SAMPLES, FRAME_SAMPLES)
             sbank.run(final=(t == T - 1), sync=False)
             if t % 4 == 3 or t == T - 1:
-                fr = sbank.poll_frames()
+                fr = sbank.poll_frames(wait=(t == T - 1))  # in flight: whatever the finished runs decoded, no waiting
                 d2h += int(fr.data.nbytes + fr.metric.nbytes + fr.payload_start.nbytes)
                 got.append(fr)
         return got
@@ -370,12 +370,18 @@ def run_sustained(args, pkg, torch, np, dev, local_rank, world, S, bank_buf, bar
     el = reduce_max_ms(time.perf_counter() - t0, dev)
     lost = sbank.frames_lost()
     n_frames = sum(f.data.shape[0] for f in frames)
+    # device time from the first run's start (its tile has landed) to the last run's end: T - 1 tiles cross PCIe in it
+    dev_ms = reduce_max_ms(sbank.last_run_ms()["total"], dev)
     out = {"workload": f"{S} streams x {T} one-frame tiles per GPU from pinned host memory ({S * FRAME_SAMPLES * 4 * T / 1e9:.0f} GB "
                        f"through a {S * 3 * FRAME_SAMPLES * 4 / 1e9:.1f} GB device ring), poll every 4 tiles",
            "value": round(world * S * FRAME_SAMPLES * T / el / 1e6, 2), "unit": UNIT, "seconds": round(el, 3),
            "value_note": "whole job (all ranks; every rank feeds its own bank from its own pinned buffer)",
            "h2d_bytes_per_gpu": int(S * FRAME_SAMPLES * 4 * T), "d2h_bytes_rank0": d2h, "frames_rank0": n_frames,
-           "frames_lost": lost, "h2d_gbs": round(world * S * FRAME_SAMPLES * 4 * T / el / 1e9, 2)}
+           "frames_lost": lost, "h2d_gbs": round(world * S * FRAME_SAMPLES * 4 * T / el / 1e9, 2),
+           "steady_h2d_gbs": round(world * S * FRAME_SAMPLES * 4 * (T - 1) / (dev_ms * 1e-3) / 1e9, 2) if T > 1 and dev_ms > 0 else None,
+           "steady_note": "tiles 2..T over the device time between the first and the last run (CUDA events): the pushes run "
+                          "back to back; `seconds` (host clock) also holds the first tile's copy, the reset and the host side "
+                          "of the final poll"}
     # parity on a sample of streams against the reference binary on the same (periodic) bytes
     if int(os.environ.get("RANK", "0")) == 0:
         from oracle import oracle as ora

@@ -140,6 +140,9 @@ int opvd_sync(opvd_handle* h);
  * metric >= 0 only; each frame is returned once, in stream order within a poll and in frame order within a
  * stream.  Only frames decoded since the last poll cross PCIe.  info may be NULL. */
 int opvd_poll_frames(opvd_handle* h, int32_t max_frames, uint8_t* frames134, opvd_frame_info* info);
+/* the same without waiting: the frames of the runs that have already finished (a live ingest loop polls with this
+ * between pushes so that the host never idles the copy engine; the reference writes its frames as they appear too) */
+int opvd_poll_frames_ready(opvd_handle* h, int32_t max_frames, uint8_t* frames134, opvd_frame_info* info);
 /* frames that were overwritten in the device log before anybody polled them (more than n_streams * max_frames
  * frames between two polls); polling continues with the oldest surviving frame */
 int opvd_frames_lost(opvd_handle* h, uint64_t* out);

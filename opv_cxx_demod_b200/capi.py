@@ -29,7 +29,7 @@ COUNTER_NAMES = ["samples", "symbols", "frames_ready", "frames_decoded", "frames
 # every symbol include/opvd.h declares (checked by tests/test_abi.py)
 EXPORTS = ["opvd_create", "opvd_destroy", "opvd_reset", "opvd_strerror", "opvd_last_cuda_error", "opvd_version",
            "opvd_push_iq", "opvd_push_iq_all", "opvd_attach_device_iq", "opvd_run", "opvd_sync",
-           "opvd_poll_frames", "opvd_frames_lost", "opvd_poll_events", "opvd_get_soft", "opvd_get_stream_info",
+           "opvd_poll_frames", "opvd_poll_frames_ready", "opvd_frames_lost", "opvd_poll_events", "opvd_get_soft", "opvd_get_stream_info",
            "opvd_get_counters", "opvd_counters_device_ptr", "opvd_last_run_ms", "opvd_demod_lanes", "opvd_stage_decode",
            "opvd_stage_decode_dev", "opvd_synth_bank", "opvd_bert_check"]
 
@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
     L.opvd_run.argtypes = [H, C.c_int]
     L.opvd_sync.argtypes = [H]
     L.opvd_poll_frames.argtypes = [H, C.c_int32, C.c_void_p, C.c_void_p]
+    L.opvd_poll_frames_ready.argtypes = [H, C.c_int32, C.c_void_p, C.c_void_p]
     L.opvd_frames_lost.argtypes = [H, C.POINTER(C.c_uint64)]
     L.opvd_poll_events.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
     L.opvd_get_soft.argtypes = [H, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]

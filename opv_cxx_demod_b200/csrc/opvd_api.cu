@@ -22,6 +22,7 @@
 #include <cstring>
 #include <deque>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/opvd.h"
@@ -575,13 +576,13 @@ int opvd_last_run_ms(opvd_handle* h, float* ms5) {
     return OPVD_OK;
 }
 
-int opvd_poll_frames(opvd_handle* h, int32_t max_frames, uint8_t* frames134, opvd_frame_info* info) {
+static int poll_frames_impl(opvd_handle* h, int32_t max_frames, uint8_t* frames134, opvd_frame_info* info, bool wait) {
     if (!h || max_frames < 0 || (max_frames > 0 && !frames134)) return OPVD_ERR_ARG;
     CK(cudaSetDevice(h->dev));
     if (!h->d_log) return 0;
     // ---- fetch what the runs enqueued so far have logged since the last poll
-    if (h->run_seq > 0) CK(cudaEventSynchronize(h->ev_back[(h->run_seq - 1) % kRuns]));
-    if (h->trace && h->run_seq > 0 && h->run_seq <= kRuns) {
+    if (wait && h->run_seq > 0) CK(cudaEventSynchronize(h->ev_back[(h->run_seq - 1) % kRuns]));
+    if (wait && h->trace && h->run_seq > 0) {
         CK(cudaStreamSynchronize(h->st_copy));
         float a = 0.f, b = 0.f;
         const cudaEvent_t base = h->tr_n > 0 ? h->tr_c0[0] : h->ev_t[0][0];
@@ -590,7 +591,7 @@ int opvd_poll_frames(opvd_handle* h, int32_t max_frames, uint8_t* frames134, opv
             cudaEventElapsedTime(&b, base, h->tr_c1[i]);
             fprintf(stderr, "opvd trace: push %d copy %.2f .. %.2f ms\n", i, a, b);
         }
-        for (long long r = 0; r < h->run_seq; ++r) {
+        for (long long r = 0; r < h->run_seq && h->run_seq <= kRuns; ++r) {  // the run events live in kRuns slots
             float t[5];
             for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], base, h->ev_t[r % kRuns][i]);
             fprintf(stderr, "opvd trace: run %lld front %.2f est %.2f demod %.2f | back track %.2f decode %.2f ms\n", r, t[0], t[1], t[2], t[3], t[4]);
@@ -611,11 +612,15 @@ int opvd_poll_frames(opvd_handle* h, int32_t max_frames, uint8_t* frames134, opv
         CK(cudaMemcpy(h->fetch.data(), h->d_log + p0, n1 * sizeof(FrameLogEntry), cudaMemcpyDeviceToHost));
         if (n_new > n1)
             CK(cudaMemcpy(h->fetch.data() + n1, h->d_log, (n_new - n1) * sizeof(FrameLogEntry), cudaMemcpyDeviceToHost));
-        std::stable_sort(h->fetch.begin(), h->fetch.end(), [](const FrameLogEntry& a, const FrameLogEntry& b) {
-            return a.stream != b.stream ? a.stream < b.stream : a.frame_idx < b.frame_idx;
-        });
-        for (const FrameLogEntry& e : h->fetch)
+        // hand them out by (stream, frame): sort 8-byte keys, not the 176-byte entries
+        std::vector<std::pair<uint64_t, uint32_t>> order(n_new);
+        for (size_t i = 0; i < n_new; ++i)
+            order[i] = {((uint64_t)(uint32_t)h->fetch[i].stream << 32) | (uint32_t)h->fetch[i].frame_idx, (uint32_t)i};
+        std::sort(order.begin(), order.end());
+        for (const auto& o : order) {
+            const FrameLogEntry& e = h->fetch[o.second];
             if (e.metric >= 0) h->pending.push_back(e);  // dropped frames (:1052) are never written by the reference
+        }
         h->polled_log = total;
     }
     int n = 0;
@@ -631,6 +636,16 @@ int opvd_poll_frames(opvd_handle* h, int32_t max_frames, uint8_t* frames134, opv
         ++n;
     }
     return n;
+}
+
+int opvd_poll_frames(opvd_handle* h, int32_t max_frames, uint8_t* frames134, opvd_frame_info* info) {
+    return poll_frames_impl(h, max_frames, frames134, info, true);
+}
+
+// the frames of the runs that have FINISHED: the log counter reaches the pinned host word at the end of every run's
+// decoder, so nothing has to be waited for and the pushes that are queued keep the copy engine busy meanwhile
+int opvd_poll_frames_ready(opvd_handle* h, int32_t max_frames, uint8_t* frames134, opvd_frame_info* info) {
+    return poll_frames_impl(h, max_frames, frames134, info, false);
 }
 
 int opvd_frames_lost(opvd_handle* h, uint64_t* out) {

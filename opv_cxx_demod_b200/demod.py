@@ -138,8 +138,10 @@ class DemodBank:
     _INFO_DTYPE = np.dtype([("stream", np.int32), ("frame_idx", np.int32), ("metric", np.int32), ("reserved", np.int32),
                             ("payload_start", np.int64), ("ready_idx", np.int64), ("sync_quality", np.float64)])
 
-    def poll_frames(self, max_frames: int | None = None) -> Frames:
-        """Frames decoded since the last poll (waits for the enqueued runs): the reference's cout.write stream."""
+    def poll_frames(self, max_frames: int | None = None, wait: bool = True) -> Frames:
+        """Frames decoded since the last poll: the reference's cout.write stream.  wait=True waits for the enqueued runs;
+        wait=False returns what the runs that have already finished decoded (opvd_poll_frames_ready)."""
+        fn = self._lib.opvd_poll_frames if wait else self._lib.opvd_poll_frames_ready
         assert self._INFO_DTYPE.itemsize == C.sizeof(capi.FrameInfo)
         chunks, infos = [], []
         cap = 65536
@@ -150,7 +152,7 @@ class DemodBank:
                 break
             buf = np.empty((want, FRAME_BYTES), np.uint8)
             info = np.empty(want, self._INFO_DTYPE)
-            n = self._ck(self._lib.opvd_poll_frames(self._h, want, buf.ctypes.data, info.ctypes.data), "opvd_poll_frames")
+            n = self._ck(fn(self._h, want, buf.ctypes.data, info.ctypes.data), "opvd_poll_frames")
             if n:
                 chunks.append(buf[:n])
                 infos.append(info[:n])

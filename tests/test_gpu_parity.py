@@ -175,6 +175,26 @@ def test_streaming_unbounded_input_ring(pkg, ora):
     bank.close()
 
 
+def test_poll_frames_ready_never_waits_and_loses_nothing(pkg, ora):
+    """opvd_poll_frames_ready between pushes (a live ingest loop: the host never waits for the device): together with one
+    final waiting poll it returns exactly the reference's frames, each once, in order."""
+    from tools import captures as cap
+
+    iq = cap.impair(cap.clean_bert(24), 78, ebn0_db=12.0, cfo_hz=250.0, lead_gap=777)
+    ref = ora.run(iq, True)
+    bank = pkg.DemodBank(1, streaming=True, max_samples=4 * 86720, max_frames=16)
+    frames = []
+    for pos in range(0, iq.shape[0], 86720):
+        bank.push_iq(0, iq[pos:pos + 86720])
+        bank.run(final=False, sync=False)
+        frames.append(bank.poll_frames(wait=False).data)
+    bank.run(final=True, sync=False)
+    frames.append(bank.poll_frames(wait=True).data)
+    assert np.array_equal(np.concatenate(frames), ref.frames)
+    assert bank.frames_lost() == 0
+    bank.close()
+
+
 @pytest.mark.parametrize("ppm", [200, -500])
 @pytest.mark.parametrize("lanes", [32, 96])
 def test_clock_offset_long_stream_small_rings(ppm, lanes, pkg, ora):
